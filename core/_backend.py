@@ -1,0 +1,808 @@
+"""ctypes binding of libtnn_b200.so (include/tnn_b200.h) and the device array type.
+
+This module is the only place the host side touches the GPU.  There is no CPU fallback: if the
+shared library is missing, cannot be loaded, or no sm_100 device is present, the first operation
+raises.  The reference's numpy calls in core/ops.py map onto the functions here one to one
+(citations in include/tnn_b200.h).
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.environ.get(
+    "TNN_B200_LIB", os.path.join(_ROOT, "tinynn-autograd_b200", "libtnn_b200.so"))
+
+F32 = np.dtype(np.float32)
+F64 = np.dtype(np.float64)
+_DT_CODE = {F32: 0, F64: 1}
+MAX_DIMS = 8
+
+# op codes (include/tnn_b200.h)
+ADD, SUB, MUL, DIV, POW, MAXIMUM, MINIMUM, GE, GT, LE, LT, EQ = range(12)
+MUL_GE, MUL_GT, MUL_LE, MUL_LT, MUL_EQ, DIV_BWD_B, POW_BWD_A, POW_BWD_B = range(20, 28)
+NEG, EXP, LOG, COPY, CLIP, SCALE, CLIP_BWD, RECIP_MUL = range(40, 48)
+RED_SUM, RED_MAX, RED_MIN = 0, 1, 2
+OPT_SGD, OPT_ADAM, OPT_RMSPROP, OPT_MOMENTUM, OPT_ADAGRAD, OPT_ADADELTA = range(6)
+
+_c_i64 = ctypes.c_int64
+_c_i32 = ctypes.c_int32
+_c_int = ctypes.c_int
+_c_vp = ctypes.c_void_p
+_c_dbl = ctypes.c_double
+_c_sz = ctypes.c_size_t
+
+_lib = None
+_inited = False
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "tnn_init": [_c_int],
+    "tnn_shutdown": [],
+    "tnn_sync": [],
+    "tnn_device_info": [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "tnn_device_count": [_c_vp],
+    "tnn_alloc": [_c_sz, _c_vp],
+    "tnn_free": [_c_vp],
+    "tnn_pool_stats": [_c_vp, _c_vp, _c_vp],
+    "tnn_pool_trim": [],
+    "tnn_h2d": [_c_vp, _c_vp, _c_sz],
+    "tnn_d2h": [_c_vp, _c_vp, _c_sz],
+    "tnn_d2d": [_c_vp, _c_vp, _c_sz],
+    "tnn_memset": [_c_vp, _c_int, _c_sz],
+    "tnn_host_alloc": [_c_sz, _c_vp],
+    "tnn_host_free": [_c_vp],
+    "tnn_h2d_async_copy_stream": [_c_vp, _c_vp, _c_sz],
+    "tnn_copy_wait_compute": [],
+    "tnn_compute_wait_copy": [],
+    "tnn_event_create": [_c_vp],
+    "tnn_event_destroy": [_c_vp],
+    "tnn_event_record": [_c_vp],
+    "tnn_event_elapsed_ms": [_c_vp, _c_vp, _c_vp],
+    "tnn_prof_enable": [_c_int],
+    "tnn_prof_collect": [_c_vp, _c_vp],
+    "tnn_l2_flush": [],
+    "tnn_ew": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+               _c_dbl, _c_dbl, _c_int],
+    "tnn_ew_flat": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_dbl, _c_dbl,
+                    _c_int],
+    "tnn_cast": [_c_int, _c_vp, _c_int, _c_vp, _c_i64],
+    "tnn_fill": [_c_int, _c_vp, _c_dbl, _c_i64],
+    "tnn_reduce": [_c_int, _c_int, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64],
+    "tnn_unbroadcast": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp],
+    "tnn_strided_copy": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp],
+    "tnn_gather_rows": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64],
+    "tnn_scatter_rows": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64],
+    "tnn_gather_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
+    "tnn_scatter_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
+    "tnn_gemm_simt": [_c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64,
+                      _c_i64, _c_i64, _c_vp, _c_int],
+    "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
+    "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
+                        _c_i64, _c_vp, _c_int],
+    "tnn_relu_fwd": [_c_int, _c_vp, _c_vp, _c_i64],
+    "tnn_relu_bwd": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
+    "tnn_colsum": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
+    "tnn_ce_stats": [_c_int, _c_vp, _c_i64, _c_i64, _c_vp],
+    "tnn_ce_merge_stats": [_c_int, _c_vp, _c_vp, _c_int],
+    "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
+    "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
+    "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
+    "tnn_nccl_unique_id": [_c_vp],
+    "tnn_nccl_init": [_c_int, _c_int, _c_vp],
+    "tnn_nccl_destroy": [],
+    "tnn_allreduce_sum": [_c_int, _c_vp, _c_i64],
+    "tnn_allgather": [_c_int, _c_vp, _c_vp, _c_i64],
+    "tnn_nccl_version": [_c_vp],
+}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["tnn_last_error", "tnn_stream", "tnn_launch_count"])
+
+
+def load_library():
+    """dlopen libtnn_b200.so and type every entry point.  Does not touch the GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BackendError(
+            "libtnn_b200.so not found at %s -- build it with `python tinynn-autograd_b200/build.py` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _c_int
+    lib.tnn_last_error.argtypes = []
+    lib.tnn_last_error.restype = ctypes.c_char_p
+    lib.tnn_stream.argtypes = []
+    lib.tnn_stream.restype = _c_vp
+    lib.tnn_launch_count.argtypes = []
+    lib.tnn_launch_count.restype = ctypes.c_uint64
+    _lib = lib
+    return lib
+
+
+def _raise(name):
+    msg = _lib.tnn_last_error().decode("utf-8", "replace")
+    raise BackendError("%s failed: %s" % (name, msg))
+
+
+def init(device=None):
+    """Bind this process to one GPU.  Called lazily by the first device operation."""
+    global _inited
+    if _inited:
+        return
+    lib = load_library()
+    if device is None:
+        device = int(os.environ.get("TNN_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if lib.tnn_init(int(device)):
+        _raise("tnn_init")
+    _inited = True
+
+
+def is_initialized():
+    return _inited
+
+
+def sync():
+    init()
+    if _lib.tnn_sync():
+        _raise("tnn_sync")
+
+
+def launch_count():
+    return int(_lib.tnn_launch_count()) if _lib is not None else 0
+
+
+def device_info():
+    init()
+    sm, maj, mnr = _c_int(), _c_int(), _c_int()
+    tot, l2 = _c_sz(), _c_sz()
+    if _lib.tnn_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr),
+                            ctypes.byref(tot), ctypes.byref(l2)):
+        _raise("tnn_device_info")
+    return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "total_mem": tot.value,
+            "l2_bytes": l2.value}
+
+
+def pool_stats():
+    a, b, c = _c_sz(), _c_sz(), _c_sz()
+    _lib.tnn_pool_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return {"reserved": a.value, "in_use": b.value, "cuda_mallocs": c.value}
+
+
+# --------------------------------------------------------------------------------------------
+# device memory
+# --------------------------------------------------------------------------------------------
+class _Buf(object):
+    """Owner of one pool block; freed back to the pool when the last view dies."""
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, nbytes):
+        out = _c_vp()
+        if _lib.tnn_alloc(nbytes, ctypes.byref(out)):
+            _raise("tnn_alloc")
+        self.ptr = out.value
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.tnn_free(self.ptr)
+        except Exception:
+            pass
+
+
+def _prod(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+class DArray(object):
+    """Contiguous row-major device array (float32 or float64)."""
+    __slots__ = ("buf", "ptr", "shape", "dtype", "size", "split", "__weakref__")
+
+    def __init__(self, buf, ptr, shape, dtype):
+        self.buf = buf
+        self.ptr = ptr
+        self.shape = shape
+        self.dtype = dtype
+        self.size = _prod(shape)
+        self.split = None  # tf32 hi/lo planes cache, see split_planes()
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    def view(self, shape, offset_elems=0):
+        shape = tuple(int(s) for s in shape)
+        return DArray(self.buf, self.ptr + offset_elems * self.dtype.itemsize, shape, self.dtype)
+
+    def numpy(self):
+        return to_numpy(self)
+
+    def __array__(self, dtype=None, copy=None):
+        a = to_numpy(self)
+        return a if dtype is None else a.astype(dtype)
+
+    def tolist(self):
+        return to_numpy(self).tolist()
+
+    def __repr__(self):
+        return "DArray(shape=%s, dtype=%s)" % (self.shape, self.dtype.name)
+
+
+def device_dtype(np_dtype):
+    """dtype policy: float32 stays float32; everything else (ints, bools, float64, Python
+    numbers) is computed in float64 so the reference's exact-equality tests hold."""
+    dt = np.dtype(np_dtype)
+    if dt == F32 or dt == np.float16:
+        return F32
+    if dt.kind in "fiub":
+        return F64
+    raise TypeError("unsupported dtype for a device tensor: %s" % dt)
+
+
+def empty(shape, dtype):
+    init()
+    shape = tuple(int(s) for s in shape)
+    dtype = np.dtype(dtype)
+    buf = _Buf(max(_prod(shape), 1) * dtype.itemsize)
+    return DArray(buf, buf.ptr, shape, dtype)
+
+
+def from_numpy(arr, dtype=None):
+    arr = np.asarray(arr)
+    dt = device_dtype(arr.dtype if dtype is None else dtype)
+    host = np.ascontiguousarray(arr, dtype=dt)
+    out = empty(host.shape, dt)
+    if host.size:
+        if _lib.tnn_h2d(out.ptr, host.ctypes.data, host.nbytes):
+            _raise("tnn_h2d")
+    return out
+
+
+def to_numpy(d):
+    out = np.empty(d.shape, dtype=d.dtype)
+    if d.size:
+        if _lib.tnn_d2h(out.ctypes.data, d.ptr, out.nbytes):
+            _raise("tnn_d2h")
+    return out
+
+
+def full(shape, value, dtype):
+    out = empty(shape, dtype)
+    if out.size:
+        if _lib.tnn_fill(_DT_CODE[out.dtype], out.ptr, float(value), out.size):
+            _raise("tnn_fill")
+    return out
+
+
+def zeros(shape, dtype):
+    out = empty(shape, dtype)
+    if out.size:
+        if _lib.tnn_memset(out.ptr, 0, out.nbytes):
+            _raise("tnn_memset")
+    return out
+
+
+def memset_zero(d):
+    if d.size and _lib.tnn_memset(d.ptr, 0, d.nbytes):
+        _raise("tnn_memset")
+
+
+def copy_into(dst, src):
+    assert dst.size == src.size and dst.dtype == src.dtype
+    if dst.size and _lib.tnn_d2d(dst.ptr, src.ptr, dst.nbytes):
+        _raise("tnn_d2d")
+
+
+def clone(d):
+    out = empty(d.shape, d.dtype)
+    copy_into(out, d)
+    return out
+
+
+def astype(d, dtype):
+    dtype = np.dtype(dtype)
+    if d.dtype == dtype:
+        return d
+    out = empty(d.shape, dtype)
+    if d.size and _lib.tnn_cast(_DT_CODE[dtype], out.ptr, _DT_CODE[d.dtype], d.ptr, d.size):
+        _raise("tnn_cast")
+    return out
+
+
+def upload_index(idx):
+    """int64 index vector -> raw device buffer (returned as a DArray typed float64 only for
+    bookkeeping; kernels read it as int64)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = empty(idx.shape, F64)
+    if idx.size and _lib.tnn_h2d(out.ptr, idx.ctypes.data, idx.nbytes):
+        _raise("tnn_h2d")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# elementwise
+# --------------------------------------------------------------------------------------------
+def _i64arr(vals):
+    return (_c_i64 * len(vals))(*vals)
+
+
+def _bstrides(shape, out_shape):
+    """element strides of a contiguous `shape` array broadcast (numpy rules) to out_shape"""
+    nd = len(out_shape)
+    pad = nd - len(shape)
+    st = [0] * nd
+    acc = 1
+    for i in range(len(shape) - 1, -1, -1):
+        if shape[i] != 1:
+            st[pad + i] = acc
+        acc *= shape[i]
+    return st
+
+
+def _common_dtype(*arrs):
+    for a in arrs:
+        if a.dtype == F64:
+            return F64
+    return F32
+
+
+def ew(op, x, y=None, z=None, p0=0.0, p1=0.0, flags=0, out=None):
+    """out = op(x, y, z) with numpy broadcasting; operands are promoted to a common dtype."""
+    ops_ = [a for a in (x, y, z) if a is not None]
+    dt = _common_dtype(*ops_)
+    ops_ = [a if a.dtype == dt else astype(a, dt) for a in ops_]
+    if len(ops_) == 1:
+        oshape = ops_[0].shape
+    else:
+        oshape = ops_[0].shape
+        for a in ops_[1:]:
+            if a.shape != oshape:
+                oshape = np.broadcast_shapes(*[a.shape for a in ops_])  # ValueError like numpy
+                break
+    if out is None:
+        out = empty(oshape, dt)
+    n = out.size
+    if n == 0:
+        return out
+    ptrs = [a.ptr for a in ops_] + [None] * (3 - len(ops_))
+    mask = 0
+    flat = True
+    for i, a in enumerate(ops_):
+        if a.size == 1:
+            mask |= 1 << i
+        elif a.shape != oshape:
+            # same element count and layout (e.g. (3,) vs (1,3)) still counts as flat
+            if a.size == n and _bstrides(a.shape, oshape) == _bstrides(oshape, oshape):
+                continue
+            flat = False
+    if flat:
+        if _lib.tnn_ew_flat(op, _DT_CODE[dt], out.ptr, ptrs[0], ptrs[1], ptrs[2], n, mask,
+                            p0, p1, flags):
+            _raise("tnn_ew_flat")
+        return out
+    nd = len(oshape)
+    if nd > MAX_DIMS:
+        raise ValueError("tensors of rank > %d are not supported" % MAX_DIMS)
+    st = [_i64arr(_bstrides(a.shape, oshape)) for a in ops_] + [None] * (3 - len(ops_))
+    if _lib.tnn_ew(op, _DT_CODE[dt], out.ptr, ptrs[0], ptrs[1], ptrs[2], nd, _i64arr(oshape),
+                   st[0], st[1], st[2], p0, p1, flags):
+        _raise("tnn_ew")
+    return out
+
+
+def add_inplace(dst, src):
+    """dst += src (same shape, same dtype)"""
+    if src.dtype != dst.dtype:
+        src = astype(src, dst.dtype)
+    if _lib.tnn_ew_flat(ADD, _DT_CODE[dst.dtype], dst.ptr, dst.ptr, src.ptr, None, dst.size,
+                        2 if (src.size == 1 and dst.size != 1) else 0, 0.0, 0.0, 0):
+        _raise("tnn_ew_flat")
+    return dst
+
+
+def broadcast_to(d, shape):
+    shape = tuple(shape)
+    if d.shape == shape:
+        return d
+    out = empty(shape, d.dtype)
+    oshape = np.broadcast_shapes(d.shape, shape)
+    if tuple(oshape) != shape:
+        raise ValueError("cannot broadcast %s to %s" % (d.shape, shape))
+    if out.size:
+        if _lib.tnn_ew(COPY, _DT_CODE[d.dtype], out.ptr, d.ptr, None, None, len(shape),
+                       _i64arr(shape), _i64arr(_bstrides(d.shape, shape)), None, None, 0.0, 0.0, 0):
+            _raise("tnn_ew")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# reductions / unbroadcast
+# --------------------------------------------------------------------------------------------
+def reduce(red_op, x, axis=None):
+    """np.sum / np.max / np.min with axis=None or an int (ops.py:225-265)"""
+    if axis is None:
+        outer, red, inner = 1, x.size, 1
+        oshape = ()
+    else:
+        nd = x.ndim
+        if not -nd <= axis < nd:
+            raise np.exceptions.AxisError(axis, nd)
+        axis %= nd
+        outer = _prod(x.shape[:axis])
+        red = x.shape[axis]
+        inner = _prod(x.shape[axis + 1:])
+        oshape = x.shape[:axis] + x.shape[axis + 1:]
+    if red == 0 and red_op != RED_SUM:
+        raise ValueError("zero-size array to reduction operation which has no identity")
+    out = empty(oshape, x.dtype)
+    if out.size:
+        if _lib.tnn_reduce(red_op, _DT_CODE[x.dtype], out.ptr, x.ptr, outer, red, inner):
+            _raise("tnn_reduce")
+    return out
+
+
+def unbroadcast(g, shape):
+    """Sum g down to `shape` exactly as the loops at ops.py:41-46 do."""
+    shape = tuple(shape)
+    if g.shape == shape:
+        return g
+    nd = g.ndim
+    lead = nd - len(shape)
+    if lead < 0:
+        raise ValueError("gradient of rank %d for a tensor of rank %d" % (nd, len(shape)))
+    keep = [0] * lead + [0 if s == 1 else 1 for s in shape]
+    for i in range(len(shape)):
+        if shape[i] != 1 and shape[i] != g.shape[lead + i]:
+            raise ValueError("operands could not be broadcast together with shapes %s %s"
+                             % (g.shape, shape))
+    out = empty(shape, g.dtype)
+    if out.size:
+        if _lib.tnn_unbroadcast(_DT_CODE[g.dtype], out.ptr, g.ptr, nd, _i64arr(g.shape),
+                                (_c_i32 * nd)(*keep)):
+            _raise("tnn_unbroadcast")
+    return out
+
+
+def colsum(g, out=None):
+    """(R, C) -> (1, C): the bias gradient"""
+    R, C = g.shape
+    if out is None:
+        out = empty((1, C), g.dtype)
+    if _lib.tnn_colsum(_DT_CODE[g.dtype], out.ptr, g.ptr, R, C):
+        _raise("tnn_colsum")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# layout
+# --------------------------------------------------------------------------------------------
+def _cstrides(shape):
+    st = [0] * len(shape)
+    acc = 1
+    for i in range(len(shape) - 1, -1, -1):
+        st[i] = acc
+        acc *= shape[i]
+    return st
+
+
+def permute(x, axes):
+    nd = x.ndim
+    axes = [a % nd for a in axes]
+    oshape = tuple(x.shape[a] for a in axes)
+    out = empty(oshape, x.dtype)
+    if out.size:
+        xs = _cstrides(x.shape)
+        if _lib.tnn_strided_copy(_DT_CODE[x.dtype], out.ptr, x.ptr, nd, _i64arr(oshape),
+                                 _i64arr(_cstrides(oshape)), _i64arr([xs[a] for a in axes])):
+            _raise("tnn_strided_copy")
+    return out
+
+
+def strided_copy(dst, dst_off, dst_strides, src, src_off, src_strides, shape):
+    if _prod(shape) == 0:
+        return
+    isz = dst.dtype.itemsize
+    if _lib.tnn_strided_copy(_DT_CODE[dst.dtype], dst.ptr + dst_off * isz, src.ptr + src_off * isz,
+                             len(shape), _i64arr(shape), _i64arr(dst_strides), _i64arr(src_strides)):
+        _raise("tnn_strided_copy")
+
+
+def gather_rows(x, idx_dev, n_idx):
+    row = _prod(x.shape[1:])
+    out = empty((n_idx,) + x.shape[1:], x.dtype)
+    if out.size and _lib.tnn_gather_rows(_DT_CODE[x.dtype], out.ptr, x.ptr, idx_dev.ptr, n_idx, row,
+                                         x.shape[0]):
+        _raise("tnn_gather_rows")
+    return out
+
+
+def scatter_rows(g, idx_dev, n_idx, shape):
+    out = zeros(shape, g.dtype)
+    row = _prod(shape[1:])
+    if g.size and _lib.tnn_scatter_rows(_DT_CODE[g.dtype], out.ptr, g.ptr, idx_dev.ptr, n_idx, row,
+                                        shape[0]):
+        _raise("tnn_scatter_rows")
+    return out
+
+
+def gather_flat(x, idx_dev, oshape):
+    out = empty(oshape, x.dtype)
+    if out.size and _lib.tnn_gather_flat(_DT_CODE[x.dtype], out.ptr, x.ptr, idx_dev.ptr, out.size):
+        _raise("tnn_gather_flat")
+    return out
+
+
+def scatter_flat(g, idx_dev, shape):
+    out = zeros(shape, g.dtype)
+    if g.size and _lib.tnn_scatter_flat(_DT_CODE[g.dtype], out.ptr, g.ptr, idx_dev.ptr, g.size):
+        _raise("tnn_scatter_flat")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------
+TC_MIN_MNK = int(os.environ.get("TNN_TC_MIN_MNK", str(1 << 26)))
+TC_ENABLED = os.environ.get("TNN_TC", "1") != "0"
+_split_epoch = 0
+
+
+def new_split_epoch():
+    """Called once per training step: tf32 planes of activations never outlive a step."""
+    global _split_epoch
+    _split_epoch += 1
+
+
+def _round4(n):
+    return (n + 3) // 4 * 4
+
+
+def split_planes(x, transposed, also_other=False):
+    """fp32 (R, C) -> tf32 (hi, lo, ld) planes; transposed=True gives the (C, R) planes.
+    Planes are cached on the array for the current step so forward and backward share them."""
+    cache = x.split
+    if cache is None or cache.get("epoch") != _split_epoch:
+        cache = {"epoch": _split_epoch}
+        x.split = cache
+    key = "t" if transposed else "p"
+    if key in cache:
+        return cache[key]
+    R, C = x.shape
+    want_p = (not transposed) or (also_other and "p" not in cache)
+    want_t = transposed or (also_other and "t" not in cache)
+    hi = lo = hit = lot = None
+    ldp = _round4(C)
+    ldt = _round4(R)
+    if want_p:
+        hi, lo = empty((R, ldp), F32), empty((R, ldp), F32)
+    if want_t:
+        hit, lot = empty((C, ldt), F32), empty((C, ldt), F32)
+    if _lib.tnn_split_tf32(x.ptr, R, C, hi.ptr if hi else None, lo.ptr if lo else None, ldp,
+                           hit.ptr if hit else None, lot.ptr if lot else None, ldt):
+        _raise("tnn_split_tf32")
+    if want_p:
+        cache["p"] = (hi, lo, ldp)
+    if want_t:
+        cache["t"] = (hit, lot, ldt)
+    return cache[key]
+
+
+def use_tensor_cores(M, N, K, dtype):
+    return (TC_ENABLED and dtype == F32 and M >= 64 and N >= 64 and K >= 32
+            and M * N * K >= TC_MIN_MNK)
+
+
+def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu=False,
+           reuse_a=False, reuse_b=False):
+    """op(a) @ op(b) (+ bias) for 2-D arrays; op = transpose when ta/tb (ops.py:150-160).
+
+    float32 products above TC_MIN_MNK run on the tcgen05 3xTF32 kernel; float64 and small or
+    odd-shaped products run on the SIMT kernel.  reuse_a/reuse_b hint that the other orientation
+    of that operand will be needed later in the step (forward -> backward), so both sets of tf32
+    planes are produced by one pass."""
+    if a.ndim != 2 or b.ndim != 2:
+        raise ValueError("matmul: only 2-D operands are supported (got %s @ %s)" % (a.shape, b.shape))
+    dt = _common_dtype(a, b)
+    if a.dtype != dt:
+        a = astype(a, dt)
+    if b.dtype != dt:
+        b = astype(b, dt)
+    M, K = (a.shape[1], a.shape[0]) if ta else a.shape
+    K2, N = (b.shape[1], b.shape[0]) if tb else b.shape
+    if K != K2:
+        raise ValueError("matmul: shapes %s and %s not aligned" % ((M, K), (K2, N)))
+    if out is None:
+        out = empty((M, N), dt)
+        accumulate = False
+    elif out.dtype != dt or out.shape != (M, N):
+        raise ValueError("matmul: bad output array")
+    if bias is not None and bias.dtype != dt:
+        bias = astype(bias, dt)
+    if M == 0 or N == 0:
+        return out
+    flags = (1 if accumulate else 0) | (2 if relu else 0)
+    if K > 0 and use_tensor_cores(M, N, K, dt):
+        a_hi, a_lo, lda = split_planes(a, transposed=ta, also_other=reuse_a)
+        b_hi, b_lo, ldb = split_planes(b, transposed=not tb, also_other=reuse_b)
+        if _lib.tnn_gemm_tf32x3(out.ptr, N, a_hi.ptr, a_lo.ptr, lda, b_hi.ptr, b_lo.ptr, ldb, M, N,
+                                K, bias.ptr if bias is not None else None, flags):
+            _raise("tnn_gemm_tf32x3")
+        return out
+    a_rs, a_cs = (1, a.shape[1]) if ta else (a.shape[1], 1)
+    b_rs, b_cs = (1, b.shape[1]) if tb else (b.shape[1], 1)
+    if _lib.tnn_gemm_simt(_DT_CODE[dt], out.ptr, N, a.ptr, a_rs, a_cs, b.ptr, b_rs, b_cs, M, N, K,
+                          bias.ptr if bias is not None else None, flags & 1):
+        _raise("tnn_gemm_simt")
+    if relu:
+        if _lib.tnn_relu_fwd(_DT_CODE[dt], out.ptr, out.ptr, out.size):
+            _raise("tnn_relu_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# fused layer / loss / optimizer kernels
+# --------------------------------------------------------------------------------------------
+def relu_fwd(x):
+    out = empty(x.shape, x.dtype)
+    if x.size and _lib.tnn_relu_fwd(_DT_CODE[x.dtype], out.ptr, x.ptr, x.size):
+        _raise("tnn_relu_fwd")
+    return out
+
+
+def relu_bwd(g, x):
+    if g.dtype != x.dtype:
+        g = astype(g, x.dtype)
+    out = empty(x.shape, x.dtype)
+    if x.size and _lib.tnn_relu_bwd(_DT_CODE[x.dtype], out.ptr, g.ptr, x.ptr, x.size):
+        _raise("tnn_relu_bwd")
+    return out
+
+
+def ce_stats(z):
+    B, C = z.shape
+    stats = empty((2,), z.dtype)
+    if _lib.tnn_ce_stats(_DT_CODE[z.dtype], z.ptr, B, C, stats.ptr):
+        _raise("tnn_ce_stats")
+    return stats
+
+
+def ce_merge_stats(stats_all, n_ranks):
+    out = empty((2,), stats_all.dtype)
+    if _lib.tnn_ce_merge_stats(_DT_CODE[stats_all.dtype], out.ptr, stats_all.ptr, n_ranks):
+        _raise("tnn_ce_merge_stats")
+    return out
+
+
+def ce_loss(z, y, stats, m_global):
+    B, C = z.shape
+    q = empty((B,), z.dtype)
+    loss = empty((), z.dtype)
+    if _lib.tnn_ce_loss(_DT_CODE[z.dtype], z.ptr, _DT_CODE[y.dtype], y.ptr, B, C, stats.ptr,
+                        float(m_global), q.ptr, loss.ptr):
+        _raise("tnn_ce_loss")
+    return loss, q
+
+
+def ce_bwd(z, y, stats, q, m_global, g):
+    B, C = z.shape
+    dz = empty((B, C), z.dtype)
+    if g.dtype != z.dtype:
+        g = astype(g, z.dtype)
+    if _lib.tnn_ce_bwd(_DT_CODE[z.dtype], dz.ptr, z.ptr, _DT_CODE[y.dtype], y.ptr, B, C, stats.ptr,
+                       q.ptr, float(m_global), g.ptr):
+        _raise("tnn_ce_bwd")
+    return dz
+
+
+def opt_step(opt, param, step_out, grad, s0, s1, hyper):
+    n = grad.size
+    h = (_c_dbl * len(hyper))(*hyper)
+    if _lib.tnn_opt_step(opt, _DT_CODE[grad.dtype], param.ptr if param is not None else None,
+                         step_out.ptr if step_out is not None else None, grad.ptr,
+                         s0.ptr if s0 is not None else None, s1.ptr if s1 is not None else None,
+                         n, h, len(hyper)):
+        _raise("tnn_opt_step")
+
+
+# --------------------------------------------------------------------------------------------
+# pinned host staging + copy stream (input prefetch), events, profiling
+# --------------------------------------------------------------------------------------------
+class PinnedArray(object):
+    """numpy array backed by cudaHostAlloc memory"""
+
+    def __init__(self, shape, dtype):
+        init()
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = max(_prod(self.shape), 1) * self.dtype.itemsize
+        p = _c_vp()
+        if _lib.tnn_host_alloc(nbytes, ctypes.byref(p)):
+            _raise("tnn_host_alloc")
+        self.ptr = p.value
+        self.nbytes = nbytes
+        raw = (ctypes.c_char * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=_prod(self.shape)).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                self.array = None
+                _lib.tnn_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def h2d_prefetch(dst, pinned):
+    """queue pinned -> dst on the copy stream, after everything queued so far on compute"""
+    if _lib.tnn_copy_wait_compute():
+        _raise("tnn_copy_wait_compute")
+    if _lib.tnn_h2d_async_copy_stream(dst.ptr, pinned.ptr, dst.nbytes):
+        _raise("tnn_h2d_async_copy_stream")
+
+
+def wait_prefetch():
+    if _lib.tnn_compute_wait_copy():
+        _raise("tnn_compute_wait_copy")
+
+
+class Event(object):
+    def __init__(self):
+        init()
+        p = _c_vp()
+        if _lib.tnn_event_create(ctypes.byref(p)):
+            _raise("tnn_event_create")
+        self.ptr = p.value
+
+    def record(self):
+        if _lib.tnn_event_record(self.ptr):
+            _raise("tnn_event_record")
+
+    def elapsed_ms_since(self, start):
+        ms = ctypes.c_float()
+        if _lib.tnn_event_elapsed_ms(start.ptr, self.ptr, ctypes.byref(ms)):
+            _raise("tnn_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.tnn_event_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def prof_enable(family):
+    init()
+    if _lib.tnn_prof_enable(family):
+        _raise("tnn_prof_enable")
+
+
+def prof_collect():
+    ms, n = _c_dbl(), ctypes.c_uint64()
+    if _lib.tnn_prof_collect(ctypes.byref(ms), ctypes.byref(n)):
+        _raise("tnn_prof_collect")
+    return ms.value, n.value
+
+
+def l2_flush():
+    init()
+    if _lib.tnn_l2_flush():
+        _raise("tnn_l2_flush")

@@ -1,0 +1,105 @@
+"""Data-parallel plumbing (new: the reference is single-process).
+
+One process per GPU.  torch.distributed (gloo) is used only as the control plane that hands the
+NCCL unique id from rank 0 to the others; every data-path collective is NCCL on this process's
+compute stream, driven through libtnn_b200.so:
+  * allreduce_sum(flat gradient arena) -- once per step, SUM (the loss already divides by the
+    global batch size, so no averaging)
+  * merge_ce_stats -- all-gather of the (max, sum-exp) pair so SoftmaxCrossEntropyLoss keeps the
+    reference's batch-global normaliser under row sharding.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+import core._backend as be
+
+_world = 1
+_rank = 0
+_nccl_ready = False
+
+
+def world_size():
+    return _world
+
+
+def rank():
+    return _rank
+
+
+def shard_bounds(n_rows, rank_, world_):
+    """rows [start, stop) of a global batch owned by a rank (contiguous, near-equal shards)"""
+    base, rem = divmod(n_rows, world_)
+    start = rank_ * base + min(rank_, rem)
+    return start, start + base + (1 if rank_ < rem else 0)
+
+
+def merge_stats_host(pairs):
+    """[(M_r, S_r)] -> (M, S) with M = max M_r, S = sum S_r * exp(M_r - M) (host mirror of
+    tnn_ce_merge_stats, used by the CPU tests of the sharding scheme)"""
+    pairs = np.asarray(pairs, dtype=np.float64).reshape(-1, 2)
+    m = pairs[:, 0].max()
+    return m, float(np.sum(pairs[:, 1] * np.exp(pairs[:, 0] - m)))
+
+
+def init_process_group(control_backend="gloo"):
+    """Read RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT (torchrun's contract), bind
+    this process to its GPU and create the NCCL communicator."""
+    global _world, _rank, _nccl_ready
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_ = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank_)))
+    be.init(local)
+    if world == 1:
+        _world, _rank = 1, 0
+        return
+    import torch.distributed as td
+    if not td.is_initialized():
+        td.init_process_group(control_backend, init_method="env://")
+    payload = [None]
+    if rank_ == 0:
+        buf = ctypes.create_string_buffer(128)
+        if be._lib.tnn_nccl_unique_id(buf):
+            be._raise("tnn_nccl_unique_id")
+        payload = [buf.raw]
+    td.broadcast_object_list(payload, src=0)
+    idbuf = ctypes.create_string_buffer(payload[0], 128)
+    if be._lib.tnn_nccl_init(rank_, world, idbuf):
+        be._raise("tnn_nccl_init")
+    _world, _rank, _nccl_ready = world, rank_, True
+
+
+def destroy_process_group():
+    global _world, _rank, _nccl_ready
+    if _nccl_ready:
+        be._lib.tnn_nccl_destroy()
+    _world, _rank, _nccl_ready = 1, 0, False
+
+
+def allreduce_sum(d):
+    """in-place SUM all-reduce of a device array on the compute stream"""
+    if _world == 1:
+        return d
+    if be._lib.tnn_allreduce_sum(be._DT_CODE[d.dtype], d.ptr, d.size):
+        be._raise("tnn_allreduce_sum")
+    return d
+
+
+def merge_ce_stats(stats):
+    """local (max, sum-exp) -> global (max, sum-exp); 2 floats per rank over NCCL"""
+    if _world == 1:
+        return stats
+    gathered = be.empty((2 * _world,), stats.dtype)
+    if be._lib.tnn_allgather(be._DT_CODE[stats.dtype], gathered.ptr, stats.ptr, 2):
+        be._raise("tnn_allgather")
+    return be.ce_merge_stats(gathered, _world)
+
+
+def barrier():
+    if _world == 1:
+        be.sync()
+        return
+    token = be.zeros((1,), be.F32)
+    allreduce_sum(token)
+    be.sync()

@@ -1,0 +1,168 @@
+"""Model: network + loss + optimiser (interface of the reference's core/model.py).
+
+step()/zero_grad() keep the reference semantics (model.py:45-68) on top of two flat device
+arenas -- one for every parameter, one for every gradient, laid out in the reference's flatten
+order (layers in order, `w` then `b`, optimizer.py:14-15):
+  * zero_grad()  = one memset of the gradient arena
+  * backward     = GEMM / column-sum kernels write parameter gradients straight into their slots
+  * step()       = (data parallel: one NCCL all-reduce of the gradient arena) + one fused
+                   optimiser kernel over the arenas
+"""
+import pickle
+
+import numpy as np
+
+import core._backend as be
+import core._dist as dist
+
+_ALIGN = 64  # elements; keeps every parameter slot 256-byte aligned for 128-bit kernels / TMA
+
+
+class Model(object):
+
+    def __init__(self, net, loss, optimizer):
+        self.net = net
+        self.loss = loss
+        self.optimizer = optimizer
+        self._phase = "TRAIN"
+        self._arena = None  # dict(params=[...], p=DArray, g=DArray, slots=[(off, size)])
+
+    def forward(self, inputs):
+        return self.net.forward(inputs)
+
+    # ------------------------------------------------------------------ checkpoint (values only)
+    def save(self, path):
+        state = [{k: v.values for k, v in layer.items() if v is not None}
+                 for layer in self.net.get_parameters()]
+        with open(path, "wb") as f:
+            pickle.dump(state, f, -1)
+        print("Model saved in %s." % path)
+
+    def load(self, path):
+        with open(path, "rb") as f:
+            state = pickle.load(f)
+        params = self.net.get_parameters()
+        if len(state) != len(params):
+            raise ValueError("Incompatible architecture: %d layers in the file, %d in the model"
+                             % (len(state), len(params)))
+        for layer, saved in zip(self.net.layers, state):
+            for k, arr in saved.items():
+                cur = layer.params.get(k)
+                if cur is not None and tuple(cur.shape) != tuple(arr.shape):
+                    raise ValueError("Incompatible architecture. %s in loaded model and %s in "
+                                     "defined model." % (arr.shape, cur.shape))
+                if cur is None:
+                    from core.tensor import Tensor
+                    layer.params[k] = Tensor(arr, requires_grad=True, dtype=arr.dtype)
+                    if hasattr(layer, "is_init"):
+                        layer.is_init = True
+                else:
+                    cur.values = arr
+                    cur.zero_grad()
+        self._arena = None
+        print("Restored model from %s." % path)
+
+    def get_phase(self):
+        return self._phase
+
+    def set_phase(self, phase):
+        assert phase in ("TRAIN", "TEST")
+        self.net.set_phase(phase)
+        self._phase = phase
+
+    # ------------------------------------------------------------------ arenas
+    def _param_list(self):
+        return [p for layer in self.net.get_parameters() for p in layer.values() if p is not None]
+
+    def _arena_valid(self, plist):
+        a = self._arena
+        if a is None or len(a["params"]) != len(plist):
+            return False
+        for p, q, (off, size) in zip(plist, a["params"], a["slots"]):
+            if p is not q or p._data.buf is not a["p"].buf or p._gslot is None:
+                return False
+            if p._data.ptr != a["p"].ptr + off * a["p"].dtype.itemsize:
+                return False
+        return True
+
+    def _build_arena(self, plist):
+        """move parameters and their gradients into flat arenas; False if they cannot share one"""
+        if not plist:
+            return False
+        dt = plist[0].dtype
+        if any(p.dtype != dt for p in plist):
+            return False
+        slots, off = [], 0
+        for p in plist:
+            slots.append((off, p._data.size))
+            off += (p._data.size + _ALIGN - 1) // _ALIGN * _ALIGN
+        pa = be.zeros((off,), dt)
+        ga = be.zeros((off,), dt)
+        for p, (o, size) in zip(plist, slots):
+            view = pa.view(p.shape, o)
+            be.copy_into(view, p._data)
+            gview = ga.view(p.shape, o)
+            had_grad = p._grad is not None and not p._grad_zero
+            if had_grad:
+                be.copy_into(gview, p._grad)
+            was_unset = p._grad is None and not p._grad_zero
+            p._data = view
+            p._host = None
+            p._gslot = gview
+            if was_unset:
+                p._grad, p._grad_zero = None, False
+            else:
+                p._grad, p._grad_zero = gview, not had_grad
+            p._grad_host = None
+        self._arena = dict(params=list(plist), p=pa, g=ga, slots=slots)
+        return True
+
+    # ------------------------------------------------------------------ training step
+    def step(self):
+        plist = self._param_list()
+        fused = self._arena_valid(plist) or self._build_arena(plist)
+        if fused and all(p._grad is p._gslot for p in plist):
+            a = self._arena
+            if dist.world_size() > 1:
+                dist.allreduce_sum(a["g"])  # SUM: 1/m_global is already inside dL/dz
+            self.optimizer.apply_fused(a["p"], a["g"])
+            for p in plist:
+                p._touch()
+                p._drop_grad()  # reference: `param += step` leaves grad = None (tensor.py:35-38)
+            return
+        self._step_generic()
+
+    def _step_generic(self):
+        """the reference's three stages verbatim (model.py:45-61), on device arrays"""
+        params = self.net.get_parameters()
+        all_grads = []
+        for param in params:
+            grad = dict()
+            for k in param:
+                p = param[k]
+                if p._grad is None:
+                    grad[k] = be.zeros(p.shape, p.dtype) if p._grad_zero else None
+                else:
+                    grad[k] = p._grad
+                if grad[k] is None:
+                    raise TypeError("parameter %r has no gradient (call zero_grad() first)" % k)
+            all_grads.append(grad)
+        if dist.world_size() > 1:
+            for grad in all_grads:
+                for g in grad.values():
+                    dist.allreduce_sum(g)
+        steps = self.optimizer.compute_step(all_grads, params)
+        for step, param in zip(steps, params):
+            for k in param:
+                param[k] += step[k]
+
+    def zero_grad(self):
+        be.new_split_epoch()
+        plist = self._param_list()
+        if plist and self._arena_valid(plist):
+            be.memset_zero(self._arena["g"])
+            for p in plist:
+                p._grad, p._grad_zero, p._grad_host = p._gslot, True, None
+            return
+        for p in plist:
+            p.zero_grad()

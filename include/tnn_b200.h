@@ -1,0 +1,209 @@
+/*
+ * tnn_b200.h -- C ABI of libtnn_b200.so, the B200 (sm_100a) execution engine behind
+ * tinynn-autograd's forward/backward tensor ops.
+ *
+ * The reference (borgwang/tinynn-autograd) has no FFI: its seam is the Python module API of
+ * core/tensor.py and core/ops.py, whose bodies are numpy calls.  Every entry point below
+ * replaces one family of those numpy call sites; the reference file:line each one stands in
+ * for is cited next to it.  The host side (core/_backend.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device pointer comes from tnn_alloc()
+ *   - every call returns 0 on success, non-zero on failure; tnn_last_error() describes it
+ *   - one process = one device = one compute stream; calls are asynchronous w.r.t. the GPU
+ *     except tnn_d2h / tnn_sync / tnn_event_elapsed_ms
+ *   - dtype: TNN_F32 = 0, TNN_F64 = 1 (reference tensors are float32 params / float64 tests)
+ *   - shapes/strides are int64 element counts, rank <= TNN_MAX_DIMS, row-major;
+ *     a stride of 0 means "broadcast along this axis" (numpy broadcasting, ops.py:32-213)
+ */
+#ifndef TNN_B200_H
+#define TNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNN_MAX_DIMS 8
+#define TNN_F32 0
+#define TNN_F64 1
+
+/* ---- elementwise op codes (tnn_ew) ------------------------------------------------------ */
+enum {
+  /* binary: out = f(x, y) */
+  TNN_OP_ADD = 0,      /* ops.py:33   add_ forward                                  */
+  TNN_OP_SUB = 1,      /* ops.py:61   sub_ (= add(neg)) fused                        */
+  TNN_OP_MUL = 2,      /* ops.py:66   mul_ forward; ops.py:72,81 grad*other          */
+  TNN_OP_DIV = 3,      /* ops.py:94   div_ forward; ops.py:100 grad/ts2              */
+  TNN_OP_POW = 4,      /* ops.py:122  pow_ forward                                   */
+  TNN_OP_MAXIMUM = 5,  /* ops.py:167  np.maximum                                     */
+  TNN_OP_MINIMUM = 6,  /* ops.py:192  np.minimum                                     */
+  TNN_OP_GE = 7,       /* tensor.py:54 __ge__  (1.0 / 0.0 in dtype)                  */
+  TNN_OP_GT = 8,       /* tensor.py:48 __gt__                                        */
+  TNN_OP_LE = 9,       /* tensor.py:57 __le__                                        */
+  TNN_OP_LT = 10,      /* tensor.py:51 __lt__                                        */
+  TNN_OP_EQ = 11,
+  /* ternary: out = f(x, y, z), x is the incoming gradient */
+  TNN_OP_MUL_GE = 20,     /* x*(y>=z)   ops.py:170 maximum_ grad ts1                 */
+  TNN_OP_MUL_GT = 21,     /* x*(y> z)   ops.py:179 maximum_ grad ts2                 */
+  TNN_OP_MUL_LE = 22,     /* x*(y<=z)   ops.py:195 minimum_ grad ts1                 */
+  TNN_OP_MUL_LT = 23,     /* x*(y< z)   ops.py:204 minimum_ grad ts2                 */
+  TNN_OP_MUL_EQ = 24,     /* x*(y==z)   ops.py:229,238 max_/min_ grad                */
+  TNN_OP_DIV_BWD_B = 25,  /* -x*y/(z*z) ops.py:109 div_ grad ts2 (y=ts1, z=ts2)      */
+  TNN_OP_POW_BWD_A = 26,  /* x*z*y**(z-1)    ops.py:128 pow_ grad ts1                */
+  TNN_OP_POW_BWD_B = 27,  /* x*(log(y)*z)    ops.py:138 pow_ grad ts2 (z = y**b)     */
+  /* unary: out = f(x) (p0, p1 are scalar parameters) */
+  TNN_OP_NEG = 40,        /* ops.py:294 neg_                                          */
+  TNN_OP_EXP = 41,        /* ops.py:217 exp_                                          */
+  TNN_OP_LOG = 42,        /* ops.py:244 log_                                          */
+  TNN_OP_COPY = 43,
+  TNN_OP_CLIP = 44,       /* ops.py:334 x.clip(p0,p1); flags bit0 = has min, bit1 = has max */
+  TNN_OP_SCALE = 45,      /* x*p0 + p1                                                */
+  TNN_OP_CLIP_BWD = 46,   /* binary: x*(mask(y; p0,p1))  ops.py:336-343               */
+  TNN_OP_RECIP_MUL = 47   /* binary: x / y -- alias of DIV kept for log_ grad ops.py:247 */
+};
+
+/* ---- reduction op codes (tnn_reduce) ------------------------------------------------------ */
+enum { TNN_RED_SUM = 0, TNN_RED_MAX = 1, TNN_RED_MIN = 2 };
+
+/* ---- optimizer codes (tnn_opt_step), core/optimizer.py ------------------------------------ */
+enum {
+  TNN_OPT_SGD = 0,      /* optimizer.py:46  */
+  TNN_OPT_ADAM = 1,     /* optimizer.py:67  */
+  TNN_OPT_RMSPROP = 2,  /* optimizer.py:107 */
+  TNN_OPT_MOMENTUM = 3, /* optimizer.py:126 */
+  TNN_OPT_ADAGRAD = 4,  /* optimizer.py:143 */
+  TNN_OPT_ADADELTA = 5  /* optimizer.py:158 */
+};
+
+/* ---- lifecycle / errors ------------------------------------------------------------------- */
+const char* tnn_last_error(void);
+int tnn_init(int device);                 /* selects the device, creates the compute + copy streams */
+int tnn_shutdown(void);
+int tnn_sync(void);                       /* cudaStreamSynchronize(compute stream) */
+int tnn_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem, size_t* l2_bytes);
+int tnn_device_count(int* n);
+void* tnn_stream(void);                   /* the cudaStream_t every kernel is launched on */
+uint64_t tnn_launch_count(void);          /* number of kernels this library has launched   */
+
+/* ---- memory: stream-ordered caching pool (replaces numpy's implicit malloc) ---------------- */
+int tnn_alloc(size_t nbytes, void** out);
+int tnn_free(void* p);
+int tnn_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* n_cuda_malloc);
+int tnn_pool_trim(void);
+int tnn_h2d(void* dst, const void* src, size_t nbytes);  /* src reusable on return */
+int tnn_d2h(void* dst, const void* src, size_t nbytes);  /* blocks until the bytes are on the host */
+int tnn_d2d(void* dst, const void* src, size_t nbytes);
+int tnn_memset(void* dst, int byte, size_t nbytes);
+int tnn_host_alloc(size_t nbytes, void** out);            /* pinned host memory */
+int tnn_host_free(void* p);
+/* copy-stream plumbing for input prefetch (run.py:78 batches overlap the previous step) */
+int tnn_h2d_async_copy_stream(void* dst, const void* pinned_src, size_t nbytes);
+int tnn_copy_wait_compute(void);          /* copy stream waits for work queued so far on compute */
+int tnn_compute_wait_copy(void);          /* compute stream waits for copies queued so far       */
+/* events on the compute stream (bench timing) */
+int tnn_event_create(void** ev);
+int tnn_event_destroy(void* ev);
+int tnn_event_record(void* ev);
+int tnn_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on stop */
+/* per-kernel-family profiling: brackets every launch of `family` with events */
+int tnn_prof_enable(int family);          /* 0 = off, 1 = tcgen05 GEMM, 2 = SIMT GEMM, 3 = tf32 split */
+int tnn_prof_collect(double* total_ms, uint64_t* n_launches); /* synchronises, then resets */
+int tnn_l2_flush(void);                   /* writes a buffer larger than L2 */
+
+/* ---- elementwise with numpy broadcasting (core/ops.py:32-249, 293-299, 333-344) ------------ */
+/* out is contiguous with shape[ndim]; xs/ys/zs are element strides (0 = broadcast); y, z may be
+ * NULL for unary/binary ops. p0/p1/flags are op parameters (clip bounds, scale). */
+int tnn_ew(int op, int dtype, void* out, const void* x, const void* y, const void* z,
+           int ndim, const int64_t* shape,
+           const int64_t* xs, const int64_t* ys, const int64_t* zs,
+           double p0, double p1, int flags);
+/* fast path: every operand is contiguous with n elements, or a single element (mask bit set) */
+int tnn_ew_flat(int op, int dtype, void* out, const void* x, const void* y, const void* z,
+                int64_t n, int scalar_mask, double p0, double p1, int flags);
+int tnn_cast(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n);
+int tnn_fill(int dtype, void* dst, double value, int64_t n);
+
+/* ---- reductions (ops.py:225-265) and the un-broadcast sum (ops.py:41-46 and 11 copies) ----- */
+/* x viewed as (outer, red, inner) contiguous; out has (outer, inner) */
+int tnn_reduce(int red_op, int dtype, void* out, const void* x,
+               int64_t outer, int64_t red, int64_t inner);
+/* grad (gshape[ndim], contiguous) summed over every axis where keep[i]==0 -> out contiguous */
+int tnn_unbroadcast(int dtype, void* out, const void* grad, int ndim,
+                    const int64_t* gshape, const int32_t* keep);
+
+/* ---- layout (ops.py:268-330) --------------------------------------------------------------- */
+/* generic strided copy: dst[doff + sum i_k*ds_k] = src[soff + sum i_k*ss_k], i in shape */
+int tnn_strided_copy(int dtype, void* dst, const void* src, int ndim, const int64_t* shape,
+                     const int64_t* dst_strides, const int64_t* src_strides);
+/* getitem_ with an int64 row-index vector (data_iterator.py:27-28): out[i,:] = x[idx[i],:] */
+int tnn_gather_rows(int dtype, void* out, const void* x, const int64_t* idx_dev,
+                    int64_t n_idx, int64_t row_elems, int64_t n_rows_src);
+/* getitem_ backward, assignment semantics (ops.py:285-288): out[idx[i],:] = g[i,:] */
+int tnn_scatter_rows(int dtype, void* out, const void* g, const int64_t* idx_dev,
+                     int64_t n_idx, int64_t row_elems, int64_t n_rows_dst);
+/* arbitrary numpy key, flattened: out[i] = x[flat_idx[i]] / out[flat_idx[i]] = g[i] */
+int tnn_gather_flat(int dtype, void* out, const void* x, const int64_t* idx_dev, int64_t n);
+int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev, int64_t n);
+
+/* ---- GEMM (ops.py:150-163 dot_: A@B, grad@B.T, A.T@grad) ----------------------------------- */
+/* SIMT path, any shape, f32/f64.  C[M,N] (ldc) = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C).
+ * A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]; flags bit0 = accumulate into C. */
+int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs, int64_t a_cs,
+                  const void* B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
+                  const void* bias, int flags);
+/* fp32 -> (hi, lo) tf32 planes for the 3xTF32 tensor-core GEMM.  x is [R, C] row-major (ld = C).
+ * plain planes  hi/lo  : [R, ldp]  (ldp >= C, multiple of 4)   -- may be NULL
+ * transposed    hiT/loT: [C, ldt]  (ldt >= R, multiple of 4)   -- may be NULL */
+int tnn_split_tf32(const float* x, int64_t R, int64_t C,
+                   float* hi, float* lo, int64_t ldp, float* hiT, float* loT, int64_t ldt);
+/* tcgen05 3xTF32: D[M,N] (ldd) = A[M,K] * B[N,K]^T with both operands K-major hi/lo planes.
+ * flags bit0 = accumulate into D, bit1 = relu on the output; bias[N] may be NULL. */
+int tnn_gemm_tf32x3(float* D, int64_t ldd,
+                    const float* a_hi, const float* a_lo, int64_t lda,
+                    const float* b_hi, const float* b_lo, int64_t ldb,
+                    int64_t M, int64_t N, int64_t K, const float* bias, int flags);
+
+/* ---- fused layer ops ----------------------------------------------------------------------- */
+/* ReLU = clip(x, 0.0) (layers.py:97-98); backward mask is x >= 0 (ops.py:336-343) */
+int tnn_relu_fwd(int dtype, void* out, const void* x, int64_t n);
+int tnn_relu_bwd(int dtype, void* dx, const void* g, const void* x, int64_t n);
+/* column sum of a (R, C) gradient = bias gradient (ops.py:49-55 on the (1,N) bias) */
+int tnn_colsum(int dtype, void* out, const void* g, int64_t R, int64_t C);
+
+/* SoftmaxCrossEntropyLoss.loss (losses.py:24-32) with its batch-GLOBAL max and normaliser.
+ * Stage 1: local max + local sum exp(z - local max) -> stats_dev[0..1] (device, dtype of z).
+ * (data parallel: all-gather stats across ranks, merge on host or with tnn_ce_merge_stats)
+ * Stage 2: given global (M, S) in stats_dev[0..1] and m = global batch:
+ *          q_i = sum_j exp(z_ij-M)/S * y_ij, loss_partial = -(1/m) sum_i ln q_i -> loss_dev[0]
+ * Backward: dz = gscale * (exp(z-M)/S - (1/m) y*exp(z-M)/(S q_i)), gscale read from g_dev[0]. */
+int tnn_ce_stats(int dtype, const void* z, int64_t B, int64_t C, void* stats_dev);
+int tnn_ce_merge_stats(int dtype, void* stats_out_dev, const void* stats_all_dev, int n_ranks);
+int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+                const void* stats_dev, double m_global, void* q_dev, void* loss_dev);
+int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev);
+
+/* fused optimizer step on flat buffers (optimizer.py:12-35 flatten + _compute_step + model.py:59-61
+ * param += step).  s0/s1 are the optimizer state vectors (Adam m,v; RMSProp ms,mom; ...), h[] the
+ * hyper-parameters:
+ *   SGD [lr]; ADAM [lr, b1, b2, eps, 1-b1^t, 1-b2^t]; RMSPROP [lr, decay, momentum, eps];
+ *   MOMENTUM [lr, momentum]; ADAGRAD [lr, eps]; ADADELTA [lr, decay, eps].
+ * param (updated in place: param += step) and step_out (receives step) may each be NULL. */
+int tnn_opt_step(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
+                 void* s1, int64_t n, const double* h, int n_h);
+
+/* ---- data-parallel collectives (new: the reference has none) -------------------- */
+int tnn_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId */
+int tnn_nccl_init(int rank, int world, const void* id128);
+int tnn_nccl_destroy(void);
+int tnn_allreduce_sum(int dtype, void* buf, int64_t n);    /* in place, compute stream */
+int tnn_allgather(int dtype, void* recv, const void* send, int64_t n_per_rank);
+int tnn_nccl_version(int* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNN_B200_H */

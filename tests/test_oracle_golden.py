@@ -1,0 +1,191 @@
+"""Pins oracle/ref_numpy.py: (a) against the known-answer vectors of the reference's own
+test/test_autograd.py (restated here from SURVEY.md 8c, citations inline) and (b) against
+tests/golden/*.npz, which oracle/make_golden.py produced by running the real reference."""
+import os
+
+import numpy as np
+import pytest
+
+import op_cases
+import ref_numpy as R
+
+F64_TOL = 1e-12
+F32_TOL = 2e-6
+
+
+def _tol(case):
+    return F32_TOL if case["dtype"] == "float32" else F64_TOL
+
+
+@pytest.fixture(scope="module")
+def gold_ops(golden_dir):
+    return np.load(os.path.join(golden_dir, "ops.npz"))
+
+
+@pytest.mark.parametrize("case", op_cases.CASES, ids=lambda c: c["name"])
+def test_oracle_matches_reference_golden(case, gold_ops):
+    out, grads = op_cases.run_oracle(case, R)
+    assert op_cases.rel_err(out, gold_ops[case["name"] + "/out"]) <= _tol(case)
+    for i, g in enumerate(grads):
+        ref = gold_ops[case["name"] + "/g%d" % i]
+        assert g.shape == ref.shape
+        assert op_cases.rel_err(g, ref) <= _tol(case)
+
+
+# ---- known-answer vectors of /root/reference/test/test_autograd.py ----------------------------
+def T(v, rg=True):
+    return R.RefTensor(v, requires_grad=rg)
+
+
+def test_add_known_answers():  # test_autograd.py:11-37
+    a, b = T([1, 3, 5]), T([5, -2, -9])
+    c = a + b
+    assert c.values.tolist() == [6, 1, -4]
+    c.backward([2, 2, 2])
+    assert a.grad.tolist() == [2, 2, 2] and b.grad.tolist() == [2, 2, 2]
+    a, b = T([[1, 3, 5], [2, 3, 0]]), T([5, -2, -9])
+    c = a + b
+    assert c.values.tolist() == [[6, 1, -4], [7, 1, -9]]
+    c.backward([[1, 1, 1], [2, 2, 2]])
+    assert a.grad.tolist() == [[1, 1, 1], [2, 2, 2]] and b.grad.tolist() == [3, 3, 3]
+    a, b = T([[1, 3, 5], [2, 3, 0]]), T([[5, -2, -9]])
+    c = a + b
+    c.backward([[1, 1, 1], [2, 2, 2]])
+    assert b.grad.tolist() == [[3, 3, 3]]
+
+
+def test_mul_div_pow_known_answers():  # test_autograd.py:40-67
+    a, b = T([1, 3, 5]), T([5, -2, -9])
+    c = a * b
+    assert c.values.tolist() == [5, -6, -45]
+    c.backward([2, 2, 2])
+    assert a.grad.tolist() == [10, -4, -18] and b.grad.tolist() == [2, 6, 10]
+    a, b = T([1, 2, 5]), T([8, -2, -10])
+    c = a / b
+    assert c.values.tolist() == [0.125, -1, -0.5]
+    c.backward([1, 1, 1])
+    assert a.grad.tolist() == [0.125, -0.5, -0.1]
+    assert b.grad.tolist() == [-0.015625, -0.5, -0.05]
+    a = T([1, -3, 5])
+    c = a ** 3
+    assert c.values.tolist() == [1, -27, 125]
+    c.backward([2, 2, 2])
+    assert a.grad.tolist() == [6, 54, 150]
+
+
+def test_dot_sum_known_answers():  # test_autograd.py:70-87
+    a = T([[1, 3, 5], [5, -2, 9]])
+    b = T([[9, 8, 9, 7], [4, 0, 3, 0], [0, 8, 2, 7]])
+    c = a @ b
+    assert c.values.tolist() == [[21, 48, 28, 42], [37, 112, 57, 98]]
+    c.backward([[1, 2, 3, 4], [4, 3, 2, 1]])
+    assert a.grad.tolist() == [[80, 13, 50], [85, 22, 35]]
+    assert b.grad.tolist() == [[21, 17, 13, 9], [-5, 0, 5, 10], [41, 37, 33, 29]]
+    a, b = T([1, 3, 5]), T([5, -2, -9])
+    s = (a + b).sum()
+    assert s.values == 3
+    s.backward(2)
+    assert a.grad.tolist() == [2, 2, 2]
+
+
+def test_exp_log_known_answers():  # test_autograd.py:90-96, 182-189 (hex goldens: SURVEY 8c)
+    a = T([1, 3, 5])
+    e = R.exp(a)
+    assert [v.hex() for v in e.values.tolist()] == [
+        "0x1.5bf0a8b145769p+1", "0x1.415e5bf6fb106p+4", "0x1.28d389970338fp+7"]
+    l = R.log(T([1, 3, 5]))
+    assert [v.hex() for v in l.values.tolist()] == [
+        "0x0.0p+0", "0x1.193ea7aad030bp+0", "0x1.9c041f7ed8d33p+0"]
+
+
+def test_max_clip_minmax_known_answers():  # test_autograd.py:129-148, 168-179, 220-229
+    t = T([[1, 3, 5], [3, 7, -2]])
+    m = R.reduce_max(t, None)
+    assert m.values == 7
+    m.backward()
+    assert t.grad.tolist() == [[0, 0, 0], [0, 1, 0]]
+    t.zero_grad()
+    m0 = R.reduce_max(t, 0)
+    assert m0.values.tolist() == [3, 7, 5]
+    m0.backward([1, 1, 1])
+    assert t.grad.tolist() == [[0, 0, 1], [1, 1, 0]]
+    a, b = T([1, 3, 5]), T([5, -2, 9])
+    mx = R.maximum(a, b)
+    assert mx.values.tolist() == [5, 3, 9]
+    mx.backward([1, 2, 1])
+    assert a.grad.tolist() == [0, 2, 0] and b.grad.tolist() == [1, 0, 1]
+    c = T([1, -3, 5])
+    r = R.clip(c, 0)
+    assert r.values.tolist() == [1, 0, 5]
+    r.backward(np.array([1, 2, 3]))
+    assert c.grad.tolist() == [1, 0, 3]
+
+
+def test_backward_enumerates_paths():  # c=b+b; d=c*c => b's vjp runs 4 times
+    calls = []
+    b = T([2.0])
+    c = b + b
+    d = c * c
+    orig = b.backward
+
+    def counting(g=None):
+        calls.append(1)
+        return orig(g)
+    b.backward = counting
+    d.backward()
+    assert len(calls) == 4
+    assert b.grad.tolist() == [16.0]  # d = 4 b^2 -> 8 b
+
+
+# ---- optimisers, trajectories ------------------------------------------------------------------
+def test_optimizers_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "optimizers.npz"))
+    makers = {
+        "sgd": lambda: R.RefSGD(0.05), "adam": lambda: R.RefAdam(1e-3),
+        "rmsprop": lambda: R.RefRMSProp(0.01, momentum=0.5),
+        "momentum": lambda: R.RefMomentum(0.02, 0.9), "adagrad": lambda: R.RefAdagrad(0.1),
+        "adadelta": lambda: R.RefAdadelta(1.0),
+    }
+    for name, make in makers.items():
+        opt = make()
+        for k in range(3):
+            step = opt._step(g["grads"][k].copy())
+            assert op_cases.rel_err(step, g[name][k]) <= F64_TOL, name
+
+
+def test_mnist_trajectory_matches_reference(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "mnist_traj.npz"))
+    np.random.seed(0)
+    x, y, onehot = R.synthetic_mnist(12800, seed=0)
+    order = np.arange(len(x))
+    np.random.shuffle(order)          # the iterator shuffles before the first (lazy-init) forward
+    xs, ys = x[order], onehot[order]
+    mlp = R.RefMLP([200, 100, 70, 30, 10], R.RefAdam(lr=1e-3))
+    losses = [float(mlp.train_step(xs[i * 128:(i + 1) * 128], ys[i * 128:(i + 1) * 128]))
+              for i in range(100)]
+    assert np.max(np.abs(np.array(losses) - gold["losses"])) <= 1e-9
+    sums = np.array([float(np.sum(p.values)) for p in mlp.params()])
+    assert np.allclose(sums, gold["final_param_sums"], rtol=1e-9, atol=1e-9)
+
+
+def test_mlp_step_matches_reference(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "mlp_step.npz"))
+    np.random.seed(0)
+    rng = np.random.RandomState(0)
+    B, D = 32, 64
+    x = rng.rand(B, D).astype(np.float32)
+    labels = np.eye(D, dtype=np.float32)[rng.randint(0, D, B)]
+    mlp = R.RefMLP([D, D, D, D], R.RefAdam(lr=1e-3))
+    losses = []
+    for it in range(3):
+        mlp.zero_grad()
+        loss = R.softmax_cross_entropy(mlp.forward(R.lift(x)), labels)
+        loss.backward()
+        if it == 0:
+            for k, p in enumerate(mlp.params()):
+                assert op_cases.rel_err(p.grad, gold["grad%d" % k]) <= 1e-10
+        mlp.step()
+        losses.append(float(loss.values))
+    assert np.max(np.abs(np.array(losses) - gold["losses"])) <= 1e-9
+    for k, p in enumerate(mlp.params()):
+        assert op_cases.rel_err(p.values, gold["param%d" % k]) <= 1e-10

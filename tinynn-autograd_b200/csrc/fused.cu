@@ -1,0 +1,526 @@
+// Fused layer / loss / optimizer kernels.
+//
+//  * ReLU forward + its `x >= 0` backward mask           layers.py:97-98, ops.py:333-344
+//  * SoftmaxCrossEntropyLoss with the reference's batch-GLOBAL max and normaliser
+//                                                        losses.py:24-32
+//  * SGD / Adam / RMSProp / Momentum / Adagrad / Adadelta on the flat parameter arena
+//                                                        optimizer.py:41-164, model.py:45-61
+// All HBM-bound streaming kernels: 128-bit accesses, grid-stride, grids in multiples of the SM
+// count.  Reductions inside the loss are two-stage and deterministic (see reduce.cu).
+#include <algorithm>
+
+#include "common.cuh"
+#include "math.cuh"
+
+namespace tnn {
+
+template <typename T>
+struct V4 {
+  static constexpr int W = sizeof(T) == 4 ? 4 : 2;
+  using type = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+  union U {
+    type v;
+    T e[W];
+  };
+};
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- ReLU ------------------------------------------------------------------------------------
+// forward: np.clip(x, 0.0, None) = maximum(x, 0) (NaN propagates); backward: g * (x >= 0)
+template <typename T, bool BWD, bool VEC>
+__global__ void __launch_bounds__(256) relu_kernel(T* out, const T* g, const T* x, int64_t n) {
+  constexpr int W = VEC ? V4<T>::W : 1;
+  const int64_t nv = n / W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    if constexpr (VEC) {
+      typename V4<T>::U a, b, r;
+      a.v = reinterpret_cast<const typename V4<T>::type*>(x)[i];
+      if (BWD) b.v = reinterpret_cast<const typename V4<T>::type*>(g)[i];
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        r.e[k] = BWD ? (a.e[k] >= T(0) ? b.e[k] : b.e[k] * T(0)) : m_max(a.e[k], T(0));
+      reinterpret_cast<typename V4<T>::type*>(out)[i] = r.v;
+    } else {
+      T a = x[i];
+      out[i] = BWD ? (a >= T(0) ? g[i] : g[i] * T(0)) : m_max(a, T(0));
+    }
+  }
+  if (VEC) {
+    int64_t t = nv * W + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+      T a = x[t];
+      out[t] = BWD ? (a >= T(0) ? g[t] : g[t] * T(0)) : m_max(a, T(0));
+    }
+  }
+}
+
+template <typename T, bool BWD>
+static int relu_launch(T* out, const T* g, const T* x, int64_t n) {
+  if (n <= 0) return 0;
+  bool vec = al16(out) && al16(x) && (!BWD || al16(g)) && n >= V4<T>::W;
+  cudaStream_t st = ctx().stream;
+  if (vec)
+    relu_kernel<T, BWD, true><<<ew_grid(ceil_div(n, V4<T>::W), 256), 256, 0, st>>>(out, g, x, n);
+  else
+    relu_kernel<T, BWD, false><<<ew_grid(n, 256), 256, 0, st>>>(out, g, x, n);
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+// ---- block reduction helpers -------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = m_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// all threads of a 256-thread block receive the result
+template <typename T, bool IS_MAX>
+__device__ __forceinline__ T block_all_reduce(T v, T* sm /* >= 8 */) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  T r = sm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = IS_MAX ? m_max(r, sm[i]) : r + sm[i];
+  return r;
+}
+
+// ---- cross entropy: stage 1 (max, sum exp) ----------------------------------------------------
+// single-CTA version for small logits matrices (the examples/mnist shape: 128 x 10)
+template <typename T>
+__global__ void __launch_bounds__(256) ce_stats_small_kernel(const T* z, int64_t n, T* stats) {
+  __shared__ T sm[8];
+  T mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += 256) mx = m_max(mx, z[i]);
+  mx = block_all_reduce<T, true>(mx, sm);
+  T s = T(0);
+  for (int64_t i = threadIdx.x; i < n; i += 256) s += m_exp(z[i] - mx);
+  s = block_all_reduce<T, false>(s, sm);
+  if (threadIdx.x == 0) {
+    stats[0] = mx;
+    stats[1] = s;
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+ce_partial_max_kernel(const T* z, int64_t n, T* partial) {
+  __shared__ T sm[8];
+  constexpr int W = VEC ? V4<T>::W : 1;
+  const int64_t nv = n / W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  T mx = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    if constexpr (VEC) {
+      typename V4<T>::U a;
+      a.v = reinterpret_cast<const typename V4<T>::type*>(z)[i];
+#pragma unroll
+      for (int k = 0; k < W; ++k) mx = m_max(mx, a.e[k]);
+    } else {
+      mx = m_max(mx, z[i]);
+    }
+  }
+  if (VEC && blockIdx.x == 0) {
+    int64_t t = nv * W + threadIdx.x;
+    if (t < n) mx = m_max(mx, z[t]);
+  }
+  mx = block_all_reduce<T, true>(mx, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = mx;
+}
+
+// every CTA first folds the per-CTA maxima (identical order everywhere), then sums its share
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+ce_partial_sumexp_kernel(const T* z, int64_t n, const T* pmax, int n_pmax, T* psum, T* stats) {
+  __shared__ T sm[8];
+  T mx = -INFINITY;
+  for (int i = threadIdx.x; i < n_pmax; i += 256) mx = m_max(mx, pmax[i]);
+  mx = block_all_reduce<T, true>(mx, sm);
+  constexpr int W = VEC ? V4<T>::W : 1;
+  const int64_t nv = n / W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  T s = T(0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    if constexpr (VEC) {
+      typename V4<T>::U a;
+      a.v = reinterpret_cast<const typename V4<T>::type*>(z)[i];
+#pragma unroll
+      for (int k = 0; k < W; ++k) s += m_exp(a.e[k] - mx);
+    } else {
+      s += m_exp(z[i] - mx);
+    }
+  }
+  if (VEC && blockIdx.x == 0) {
+    int64_t t = nv * W + threadIdx.x;
+    if (t < n) s += m_exp(z[t] - mx);
+  }
+  s = block_all_reduce<T, false>(s, sm);
+  if (threadIdx.x == 0) {
+    psum[blockIdx.x] = s;
+    if (blockIdx.x == 0) stats[0] = mx;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fold_sum_kernel(const T* psum, int n_psum, T* dst) {
+  __shared__ T sm[8];
+  T s = T(0);
+  for (int i = threadIdx.x; i < n_psum; i += 256) s += psum[i];
+  s = block_all_reduce<T, false>(s, sm);
+  if (threadIdx.x == 0) dst[0] = s;
+}
+
+// merge per-rank (max, sumexp) pairs: M = max M_r, S = sum S_r * exp(M_r - M)
+template <typename T>
+__global__ void ce_merge_stats_kernel(T* out, const T* all, int n_ranks) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    T mx = -INFINITY;
+    for (int r = 0; r < n_ranks; ++r) mx = m_max(mx, all[2 * r]);
+    T s = T(0);
+    for (int r = 0; r < n_ranks; ++r) s += all[2 * r + 1] * m_exp(all[2 * r] - mx);
+    out[0] = mx;
+    out[1] = s;
+  }
+}
+
+// ---- cross entropy: stage 2 (per-row q_i, -ln q_i) ---------------------------------------------
+// one warp per row; q_i = sum_j (exp(z_ij - M) / S) * y_ij   (losses.py:27-28)
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const T* z, const TY* y, int64_t B, int64_t C, const T* stats, T* q, T* nll) {
+  const T mx = stats[0], S = stats[1];
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < B; r += warps_total) {
+    const T* zr = z + r * C;
+    const TY* yr = y + r * C;
+    T acc = T(0);
+    for (int64_t j = lane; j < C; j += 32) {
+      TY yy = yr[j];
+      if (yy != TY(0)) acc += (m_exp(zr[j] - mx) / S) * (T)yy;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      q[r] = acc;
+      nll[r] = -m_log(acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_fold_loss_kernel(const T* nll, int64_t B, T m, T* loss) {
+  __shared__ T sm[8];
+  T s = T(0);
+  for (int64_t i = threadIdx.x; i < B; i += 256) s += nll[i];
+  s = block_all_reduce<T, false>(s, sm);
+  if (threadIdx.x == 0) loss[0] = s / m;
+}
+
+// ---- cross entropy backward ---------------------------------------------------------------------
+// dz_kl = g * ( e_kl/S - (1/m) * y_kl * e_kl / (S * q_k) ),  e = exp(z - M)
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats, const T* q,
+              T m, const T* gptr) {
+  // rows over blockIdx.y, columns over blockIdx.x * 256 + threadIdx.x: no per-element division
+  const T mx = stats[0], S = stats[1], g = gptr[0];
+  for (int64_t r = blockIdx.y; r < B; r += gridDim.y) {
+    const T qm = q[r] * m;
+    const T* zr = z + r * C;
+    const TY* yr = y + r * C;
+    T* dr = dz + r * C;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
+      T p = m_exp(zr[c] - mx) / S;
+      T yy = (T)yr[c];
+      T v = p;
+      if (yy != T(0)) v = p - (yy * p) / qm;
+      dr[c] = g * v;
+    }
+  }
+}
+
+// ---- optimizers ------------------------------------------------------------------------------
+struct OptH {
+  double h[8];
+};
+
+template <int OPT, typename T>
+__global__ void __launch_bounds__(256)
+opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH hh) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T g = grad[i];
+    T step;
+    if constexpr (OPT == TNN_OPT_SGD) {
+      step = -(T)hh.h[0] * g;
+    } else if constexpr (OPT == TNN_OPT_ADAM) {
+      const T lr = (T)hh.h[0], b1 = (T)hh.h[1], b2 = (T)hh.h[2], eps = (T)hh.h[3];
+      const T bc1 = (T)hh.h[4], bc2 = (T)hh.h[5];
+      T m = s0[i], v = s1[i];
+      m += (T(1) - b1) * (g - m);
+      v += (T(1) - b2) * (g * g - v);
+      s0[i] = m;
+      s1[i] = v;
+      T mh = m / bc1, vh = v / bc2;
+      step = -lr * mh / (m_sqrt(vh) + eps);
+    } else if constexpr (OPT == TNN_OPT_RMSPROP) {
+      const T lr = (T)hh.h[0], decay = (T)hh.h[1], mom_c = (T)hh.h[2], eps = (T)hh.h[3];
+      T ms = s0[i], mom = s1[i];
+      ms += (T(1) - decay) * (g * g - ms);
+      mom = mom_c * mom + lr * g / m_sqrt(ms + eps);
+      s0[i] = ms;
+      s1[i] = mom;
+      step = -mom;
+    } else if constexpr (OPT == TNN_OPT_MOMENTUM) {
+      const T lr = (T)hh.h[0], mom_c = (T)hh.h[1];
+      T acc = mom_c * s0[i] + g;
+      s0[i] = acc;
+      step = -lr * acc;
+    } else if constexpr (OPT == TNN_OPT_ADAGRAD) {
+      const T lr = (T)hh.h[0], eps = (T)hh.h[1];
+      T G = s0[i] + g * g;
+      s0[i] = G;
+      step = -(lr / m_sqrt(G + eps)) * g;
+    } else {  // ADADELTA
+      const T lr = (T)hh.h[0], decay = (T)hh.h[1], eps = (T)hh.h[2];
+      T Eg = s0[i], delta = s1[i];
+      Eg += (T(1) - decay) * (g * g - Eg);
+      T sd = m_sqrt(delta + eps);
+      T d = g * (sd / m_sqrt(Eg + eps));
+      step = -lr * d;
+      delta += (T(1) - decay) * (d * d - delta);
+      s0[i] = Eg;
+      s1[i] = delta;
+    }
+    if (step_out) step_out[i] = step;
+    if (param) param[i] += step;
+  }
+}
+
+// Adam is the hot one (28 B/param): 128-bit variant
+template <typename T>
+__global__ void __launch_bounds__(256)
+adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh) {
+  using VT = typename V4<T>::type;
+  using U = typename V4<T>::U;
+  constexpr int W = V4<T>::W;
+  const T lr = (T)hh.h[0], b1 = (T)hh.h[1], b2 = (T)hh.h[2], eps = (T)hh.h[3];
+  const T bc1 = (T)hh.h[4], bc2 = (T)hh.h[5];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    U g, m, v, p;
+    g.v = reinterpret_cast<const VT*>(grad)[i];
+    m.v = reinterpret_cast<const VT*>(s0)[i];
+    v.v = reinterpret_cast<const VT*>(s1)[i];
+    p.v = reinterpret_cast<const VT*>(param)[i];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      m.e[k] += (T(1) - b1) * (g.e[k] - m.e[k]);
+      v.e[k] += (T(1) - b2) * (g.e[k] * g.e[k] - v.e[k]);
+      T mh = m.e[k] / bc1, vh = v.e[k] / bc2;
+      p.e[k] += -lr * mh / (m_sqrt(vh) + eps);
+    }
+    reinterpret_cast<VT*>(s0)[i] = m.v;
+    reinterpret_cast<VT*>(s1)[i] = v.v;
+    reinterpret_cast<VT*>(param)[i] = p.v;
+  }
+}
+
+template <typename T>
+static int opt_dispatch(int opt, T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n,
+                        const OptH& hh) {
+  cudaStream_t st = ctx().stream;
+  int grid = ew_grid(n, 256);
+  switch (opt) {
+    case TNN_OPT_SGD:
+      opt_kernel<TNN_OPT_SGD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      break;
+    case TNN_OPT_ADAM: {
+      constexpr int W = V4<T>::W;
+      if (param && !step_out && al16(param) && al16(grad) && al16(s0) && al16(s1) && n >= W) {
+        int64_t nv = n / W;
+        adam_vec_kernel<T><<<ew_grid(nv, 256), 256, 0, st>>>(param, grad, s0, s1, nv, hh);
+        TNN_POST_LAUNCH();
+        int64_t done = nv * W;
+        if (done < n)
+          opt_kernel<TNN_OPT_ADAM, T><<<1, 256, 0, st>>>(param + done, nullptr, grad + done,
+                                                         s0 + done, s1 + done, n - done, hh);
+        else
+          return 0;
+      } else {
+        opt_kernel<TNN_OPT_ADAM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      }
+      break;
+    }
+    case TNN_OPT_RMSPROP:
+      opt_kernel<TNN_OPT_RMSPROP, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      break;
+    case TNN_OPT_MOMENTUM:
+      opt_kernel<TNN_OPT_MOMENTUM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      break;
+    case TNN_OPT_ADAGRAD:
+      opt_kernel<TNN_OPT_ADAGRAD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      break;
+    case TNN_OPT_ADADELTA:
+      opt_kernel<TNN_OPT_ADADELTA, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      break;
+    default:
+      TNN_FAIL("tnn_opt_step: unknown optimizer code");
+  }
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+// ---- CE host drivers ---------------------------------------------------------------------------
+template <typename T>
+static int ce_stats_impl(const T* z, int64_t B, int64_t C, T* stats) {
+  const int64_t n = B * C;
+  if (n <= 0) TNN_FAIL("tnn_ce_stats: empty logits");
+  cudaStream_t st = ctx().stream;
+  if (n <= 16384) {
+    ce_stats_small_kernel<T><<<1, 256, 0, st>>>(z, n, stats);
+    TNN_POST_LAUNCH();
+    return 0;
+  }
+  const bool vec = al16(z);
+  const int W = vec ? V4<T>::W : 1;
+  int grid = ew_grid(ceil_div(n, W), 256, 4);
+  void* scratch;
+  if (get_scratch((size_t)grid * 2 * sizeof(T), &scratch)) return 1;
+  T* pmax = (T*)scratch;
+  T* psum = pmax + grid;
+  if (vec) ce_partial_max_kernel<T, true><<<grid, 256, 0, st>>>(z, n, pmax);
+  else ce_partial_max_kernel<T, false><<<grid, 256, 0, st>>>(z, n, pmax);
+  TNN_POST_LAUNCH();
+  if (vec) ce_partial_sumexp_kernel<T, true><<<grid, 256, 0, st>>>(z, n, pmax, grid, psum, stats);
+  else ce_partial_sumexp_kernel<T, false><<<grid, 256, 0, st>>>(z, n, pmax, grid, psum, stats);
+  TNN_POST_LAUNCH();
+  ce_fold_sum_kernel<T><<<1, 256, 0, st>>>(psum, grid, stats + 1);
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+template <typename T, typename TY>
+static int ce_loss_impl(const T* z, const TY* y, int64_t B, int64_t C, const T* stats, double m,
+                        T* q, T* loss) {
+  cudaStream_t st = ctx().stream;
+  void* scratch;
+  if (get_scratch((size_t)B * sizeof(T), &scratch)) return 1;
+  T* nll = (T*)scratch;
+  int grid = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)ctx().sm_count * 8);
+  ce_rows_kernel<T, TY><<<grid, 256, 0, st>>>(z, y, B, C, stats, q, nll);
+  TNN_POST_LAUNCH();
+  ce_fold_loss_kernel<T><<<1, 256, 0, st>>>(nll, B, (T)m, loss);
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+template <typename T, typename TY>
+static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats,
+                       const T* q, double m, const T* g) {
+  cudaStream_t st = ctx().stream;
+  int gx = (int)std::min<int64_t>(ceil_div(C, 256), 64);
+  int64_t gy = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)ctx().sm_count * 8 / gx));
+  if (gy > 65535) gy = 65535;
+  ce_bwd_kernel<T, TY><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace tnn
+
+using namespace tnn;
+
+extern "C" {
+
+int tnn_relu_fwd(int dtype, void* out, const void* x, int64_t n) {
+  TNN_REQUIRE_INIT();
+  if (dtype == TNN_F32) return relu_launch<float, false>((float*)out, nullptr, (const float*)x, n);
+  if (dtype == TNN_F64) return relu_launch<double, false>((double*)out, nullptr, (const double*)x, n);
+  TNN_FAIL("tnn_relu_fwd: bad dtype");
+}
+
+int tnn_relu_bwd(int dtype, void* dx, const void* g, const void* x, int64_t n) {
+  TNN_REQUIRE_INIT();
+  if (dtype == TNN_F32) return relu_launch<float, true>((float*)dx, (const float*)g, (const float*)x, n);
+  if (dtype == TNN_F64) return relu_launch<double, true>((double*)dx, (const double*)g, (const double*)x, n);
+  TNN_FAIL("tnn_relu_bwd: bad dtype");
+}
+
+int tnn_ce_stats(int dtype, const void* z, int64_t B, int64_t C, void* stats_dev) {
+  TNN_REQUIRE_INIT();
+  if (dtype == TNN_F32) return ce_stats_impl<float>((const float*)z, B, C, (float*)stats_dev);
+  if (dtype == TNN_F64) return ce_stats_impl<double>((const double*)z, B, C, (double*)stats_dev);
+  TNN_FAIL("tnn_ce_stats: bad dtype");
+}
+
+int tnn_ce_merge_stats(int dtype, void* stats_out_dev, const void* stats_all_dev, int n_ranks) {
+  TNN_REQUIRE_INIT();
+  cudaStream_t st = ctx().stream;
+  if (dtype == TNN_F32)
+    ce_merge_stats_kernel<float><<<1, 32, 0, st>>>((float*)stats_out_dev, (const float*)stats_all_dev, n_ranks);
+  else if (dtype == TNN_F64)
+    ce_merge_stats_kernel<double><<<1, 32, 0, st>>>((double*)stats_out_dev, (const double*)stats_all_dev, n_ranks);
+  else
+    TNN_FAIL("tnn_ce_merge_stats: bad dtype");
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+                const void* stats_dev, double m_global, void* q_dev, void* loss_dev) {
+  TNN_REQUIRE_INIT();
+  if (B <= 0 || C <= 0) TNN_FAIL("tnn_ce_loss: empty logits");
+  if (dtype == TNN_F32 && y_dtype == TNN_F32)
+    return ce_loss_impl<float, float>((const float*)z, (const float*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev);
+  if (dtype == TNN_F32 && y_dtype == TNN_F64)
+    return ce_loss_impl<float, double>((const float*)z, (const double*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev);
+  if (dtype == TNN_F64 && y_dtype == TNN_F64)
+    return ce_loss_impl<double, double>((const double*)z, (const double*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev);
+  if (dtype == TNN_F64 && y_dtype == TNN_F32)
+    return ce_loss_impl<double, float>((const double*)z, (const float*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev);
+  TNN_FAIL("tnn_ce_loss: bad dtype");
+}
+
+int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev) {
+  TNN_REQUIRE_INIT();
+  if (B <= 0 || C <= 0) return 0;
+  if (dtype == TNN_F32 && y_dtype == TNN_F32)
+    return ce_bwd_impl<float, float>((float*)dz, (const float*)z, (const float*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev);
+  if (dtype == TNN_F32 && y_dtype == TNN_F64)
+    return ce_bwd_impl<float, double>((float*)dz, (const float*)z, (const double*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev);
+  if (dtype == TNN_F64 && y_dtype == TNN_F64)
+    return ce_bwd_impl<double, double>((double*)dz, (const double*)z, (const double*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev);
+  if (dtype == TNN_F64 && y_dtype == TNN_F32)
+    return ce_bwd_impl<double, float>((double*)dz, (const double*)z, (const float*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev);
+  TNN_FAIL("tnn_ce_bwd: bad dtype");
+}
+
+int tnn_opt_step(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
+                 void* s1, int64_t n, const double* h, int n_h) {
+  TNN_REQUIRE_INIT();
+  if (n <= 0) return 0;
+  if (n_h < 0 || n_h > 8) TNN_FAIL("tnn_opt_step: at most 8 hyper-parameters");
+  OptH hh;
+  for (int i = 0; i < 8; ++i) hh.h[i] = i < n_h ? h[i] : 0.0;
+  if (dtype == TNN_F32)
+    return opt_dispatch<float>(opt, (float*)param, (float*)step_out, (const float*)grad, (float*)s0, (float*)s1, n, hh);
+  if (dtype == TNN_F64)
+    return opt_dispatch<double>(opt, (double*)param, (double*)step_out, (const double*)grad, (double*)s0, (double*)s1, n, hh);
+  TNN_FAIL("tnn_opt_step: bad dtype");
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// SIMT GEMM for ops.py:150-163 (dot_: A@B, grad@B.T, A.T@grad) on shapes the tensor-core path
+// cannot or should not take: float64 (the reference's test path), and the small / odd-sized
+// layers of the examples/mnist MLP (70-, 30-, 10-wide: row pitches of 280/120/40 bytes break
+// TMA's 16-byte stride rule).  Operands are addressed through (row, col) element strides so the
+// transposed products of the backward pass read the original buffers in place.
+//
+// C[M,N] = A[M,K] * B[K,N] (+ bias[N]) (+ C), shared-memory tiled, register-blocked, the next
+// K-slab prefetched into registers while the current one is multiplied.  Deterministic: each
+// output element is accumulated by one thread in k order.
+#include "common.cuh"
+
+namespace tnn {
+
+template <typename T, int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_t a_rs, int64_t a_cs,
+                 const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
+                 const T* __restrict__ bias, int flags) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int A_PER = (BM * BK) / NT;
+  constexpr int B_PER = (BK * BN) / NT;
+  static_assert((BM * BK) % NT == 0 && (BK * BN) % NT == 0, "tile/threads mismatch");
+  __shared__ T As[BK][BM + 1];
+  __shared__ T Bs[BK][BN + 1];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const bool a_kfast = (a_cs == 1);   // k contiguous in memory
+  const bool b_nfast = (b_cs == 1);   // n contiguous in memory
+
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  T ra[A_PER], rb[B_PER];
+
+  auto load_tiles = [&](int64_t k0) {
+#pragma unroll
+    for (int e = 0; e < A_PER; ++e) {
+      int idx = tid + e * NT;
+      int m = a_kfast ? idx / BK : idx % BM;
+      int k = a_kfast ? idx % BK : idx / BM;
+      int64_t gm = m0 + m, gk = k0 + k;
+      ra[e] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : T(0);
+    }
+#pragma unroll
+    for (int e = 0; e < B_PER; ++e) {
+      int idx = tid + e * NT;
+      int k = b_nfast ? idx / BN : idx % BK;
+      int n = b_nfast ? idx % BN : idx / BK;
+      int64_t gk = k0 + k, gn = n0 + n;
+      rb[e] = (gk < K && gn < N) ? B[gk * b_rs + gn * b_cs] : T(0);
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int e = 0; e < A_PER; ++e) {
+      int idx = tid + e * NT;
+      int m = a_kfast ? idx / BK : idx % BM;
+      int k = a_kfast ? idx % BK : idx / BM;
+      As[k][m] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < B_PER; ++e) {
+      int idx = tid + e * NT;
+      int k = b_nfast ? idx / BN : idx % BK;
+      int n = b_nfast ? idx % BN : idx / BK;
+      Bs[k][n] = rb[e];
+    }
+  };
+
+  load_tiles(0);
+  for (int64_t k0 = 0; k0 < K; k0 += BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + BK < K) load_tiles(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+
+  const bool accumulate = flags & 1;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int64_t gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      T v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (accumulate) v += C[gm * ldc + gn];
+      C[gm * ldc + gn] = v;
+    }
+  }
+}
+
+template <typename T>
+static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
+                          int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
+                          const T* bias, int flags) {
+  if (M <= 0 || N <= 0) return 0;
+  cudaStream_t st = ctx().stream;
+  prof_begin(2);
+  int64_t tiles64 = ceil_div(M, 64) * ceil_div(N, 64);
+  if (tiles64 >= ctx().sm_count) {
+    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+    if (grid.y > 65535) TNN_FAIL("tnn_gemm_simt: M too large for the SIMT path");
+    gemm_simt_kernel<T, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags);
+  } else {
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
+    gemm_simt_kernel<T, 32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags);
+  }
+  TNN_POST_LAUNCH();
+  prof_end(2);
+  return 0;
+}
+
+}  // namespace tnn
+
+using namespace tnn;
+
+extern "C" int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs,
+                             int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, int64_t M,
+                             int64_t N, int64_t K, const void* bias, int flags) {
+  TNN_REQUIRE_INIT();
+  if (M < 0 || N < 0 || K < 0) TNN_FAIL("tnn_gemm_simt: negative extent");
+  if (dtype == TNN_F32)
+    return gemm_simt_impl<float>((float*)C, ldc, (const float*)A, a_rs, a_cs, (const float*)B, b_rs,
+                                 b_cs, M, N, K, (const float*)bias, flags);
+  if (dtype == TNN_F64)
+    return gemm_simt_impl<double>((double*)C, ldc, (const double*)A, a_rs, a_cs, (const double*)B,
+                                  b_rs, b_cs, M, N, K, (const double*)bias, flags);
+  TNN_FAIL("tnn_gemm_simt: dtype must be TNN_F32 or TNN_F64");
+}

@@ -1,0 +1,596 @@
+// Tensor-core GEMM for ops.py:150-163 (dot_: A@B, grad@B.T, A.T@grad) in fp32-accurate 3xTF32:
+//
+//     x = hi + lo,  hi = tf32(x), lo = tf32(x - hi)
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (fp32 accumulation in TMEM)
+//
+// Pipeline (sm_100a only):
+//   tnn_split_tf32   one pass over an fp32 matrix -> hi/lo planes, optionally also transposed,
+//                    so every product of the forward/backward pass becomes the one canonical
+//                    form below (both operands K-major).
+//   tnn_gemm_tf32x3  D[M,N] = A[M,K] * B[N,K]^T.  Persistent, warp-specialised:
+//                      warp 0    TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier tx)
+//                      warp 1    MMA issuer    (tcgen05.mma.kind::tf32, 3 MMAs per K=8 step)
+//                      warps 2-5 epilogue      (tcgen05.ld TMEM -> regs -> +bias/relu/accumulate)
+//                    Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue
+//                    of tile i overlaps the main loop of tile i+1.
+//                    CG = 1: one CTA per SM, tile 128 x 256.
+//                    CG = 2: CTA pair (cta_group::2), tile 256 x 256, each CTA stages its own
+//                            128 rows of A and half of B -> half the L2->SMEM operand traffic
+//                            per flop and room for a third pipeline stage.
+// Algorithmic work: 2*M*N*K flop per call; the tensor pipe executes 3x that in TF32.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace tnn {
+namespace tc {
+
+constexpr int BK = 32;                    // fp32 elements per K block = 128 bytes = swizzle row
+constexpr int ROWS_A = 128;               // A rows staged per CTA
+constexpr int UMMA_N = 256;               // accumulator columns per tile
+constexpr int UMMA_K = 8;                 // tf32
+constexpr int PLANE_ROW_BYTES = BK * 4;   // 128
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+template <int CG>
+struct Cfg {
+  static constexpr int ROWS_B = UMMA_N / CG;                      // B rows staged per CTA
+  static constexpr int STAGES = CG == 1 ? 2 : 3;
+  static constexpr int A_BYTES = ROWS_A * PLANE_ROW_BYTES;        // one plane
+  static constexpr int B_BYTES = ROWS_B * PLANE_ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo of both operands
+  static constexpr int TILE_M = ROWS_A * CG;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  printf("tnn gemm_tc: mbarrier wait timed out (block %d thread %d bar %x parity %u)\n",
+         (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+               ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  } else {
+    // both CTAs of the pair signal the leader's barrier (peer bit cleared)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_relinquish() {
+  if constexpr (CG == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit all prior MMAs of this thread to an mbarrier (implies fence::before_thread_sync)
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N, M
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the GEMM kernel ---------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                   const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi,
+                   const __grid_constant__ CUtensorMap map_b_lo,
+                   float* __restrict__ D, int64_t ldd, int M, int N, int K,
+                   const float* __restrict__ bias, int flags) {
+  using C = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp of every CTA in the group
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int tiles_m = (M + C::TILE_M - 1) / C::TILE_M;
+  const int tiles_n = (N + UMMA_N - 1) / UMMA_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int group = blockIdx.x / CG;            // CTA (pair) index
+  const int num_groups = gridDim.x / CG;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = group; t < num_tiles; t += num_groups) {
+        const int tm = t / tiles_n, tn = t % tiles_n;
+        const int row_a = tm * C::TILE_M + (int)cta_rank * ROWS_A;
+        const int row_b = tn * UMMA_N + (int)cta_rank * C::ROWS_B;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sa_lo = sa_hi + C::A_BYTES;
+          const uint32_t sb_hi = sa_lo + C::A_BYTES;
+          const uint32_t sb_lo = sb_hi + C::B_BYTES;
+          if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)C::STAGE_BYTES * CG);
+          const int k0 = kb * BK;
+          tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
+          tma_load_2d<CG>(sa_lo, &map_a_lo, full_bar(stage), k0, row_a);
+          tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
+          tma_load_2d<CG>(sb_lo, &map_b_lo, full_bar(stage), k0, row_b);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(C::TILE_M, UMMA_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = group; t < num_tiles; t += num_groups) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sa_lo = sa_hi + C::A_BYTES;
+          const uint32_t sb_hi = sa_lo + C::A_BYTES;
+          const uint32_t sb_lo = sb_hi + C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = (uint32_t)(k * UMMA_K * 4);  // bytes inside the 128-byte row
+            const uint64_t da_hi = make_smem_desc(sa_hi + koff);
+            const uint64_t da_lo = make_smem_desc(sa_lo + koff);
+            const uint64_t db_hi = make_smem_desc(sb_hi + koff);
+            const uint64_t db_lo = make_smem_desc(sb_lo + koff);
+            // small terms first
+            umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
+            umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
+          }
+          umma_commit<CG>(empty_bar(stage));          // frees the smem slot when the MMAs retire
+          if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool accumulate = flags & 1, relu = flags & 2;
+    for (int t = group; t < num_tiles; t += num_groups) {
+      const int tm = t / tiles_n, tn = t % tiles_n;
+      const int row = tm * C::TILE_M + (int)cta_rank * ROWS_A + quad * 32 + lane;
+      const int col0 = tn * UMMA_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * UMMA_N);
+      float* drow = D + (int64_t)row * ldd;
+#pragma unroll 1
+      for (int c = 0; c < UMMA_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int col = col0 + c;
+        if (row < M && col < N) {
+          if (col + 32 <= N && ((reinterpret_cast<uintptr_t>(drow + col) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              if (bias) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + col + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(drow + col + j);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(drow + col + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col + j < N) {
+                float v = __uint_as_float(r[j]);
+                if (bias) v += bias[col + j];
+                if (accumulate) v += drow[col + j];
+                if (relu) v = fmaxf(v, 0.f);
+                drow[col + j] = v;
+              }
+            }
+          }
+        }
+      }
+      // this warp is done reading the accumulator: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  // teardown: everyone (both CTAs of a pair) must be done before TMEM goes away.  The single-lane
+  // roles re-converge first: the cluster barrier and tcgen05.dealloc are .aligned instructions.
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- fp32 -> tf32 hi/lo split (+ optional transposed copy) ----------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// 64 x 64 tile per CTA, 256 threads; plain planes are written with 128-bit stores straight from
+// registers, the transposed planes go through a padded shared-memory tile so both global sides
+// stay coalesced.
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __restrict__ hi,
+                  float* __restrict__ lo, int64_t ldp, float* __restrict__ hiT,
+                  float* __restrict__ loT, int64_t ldt, int vec_in) {
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16, each thread 4 cols x 4 rows
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int lr = ty + 16 * i;
+    const int64_t r = r0 + lr, c = c0 + tx * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      if (vec_in && c + 3 < C) {
+        const float4 t = *reinterpret_cast<const float4*>(x + r * C + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c + k < C) v[k] = x[r * C + c + k];
+      }
+      if (hi) {
+        float h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h[k] = to_tf32(v[k]);
+          l[k] = to_tf32(v[k] - h[k]);
+        }
+        // ldp is a multiple of 4 and c is a multiple of 4: 16-byte aligned; columns in
+        // [C, ldp) receive zeros (TMA never reads them, the tensor map ends at C)
+        if (c < ldp) {
+          *reinterpret_cast<float4*>(hi + r * ldp + c) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(lo + r * ldp + c) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+    if (hiT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tile[lr][tx * 4 + k] = v[k];
+    }
+  }
+  if (!hiT) return;
+  __syncthreads();
+  // transposed: output row = source column; each thread writes 4 consecutive source rows
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int lc = ty + 16 * i;            // source column inside the tile
+    const int64_t c = c0 + lc, r = r0 + tx * 4;
+    if (c < C && r < ldt) {
+      float h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = tile[tx * 4 + k][lc];   // zero beyond R
+        h[k] = to_tf32(v);
+        l[k] = to_tf32(v - h[k]);
+      }
+      *reinterpret_cast<float4*>(hiT + c * ldt + r) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(loT + c * ldt + r) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  TNN_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) TNN_FAIL("cuTensorMapEncodeTiled is not available");
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return 0;
+}
+
+// 2-D fp32 tensor [rows, K] with row pitch ld (elements); box = [BK, box_rows], 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) TNN_FAIL("tf32x3 GEMM: operand plane must be 16-byte aligned");
+  if (ld % 4 != 0) TNN_FAIL("tf32x3 GEMM: operand pitch must be a multiple of 4 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TNN_FAIL("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return 0;
+}
+
+static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (TNN_GEMM_CG)
+static bool g_attr_set[3] = {false, false, false};
+
+template <int CG>
+static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
+                       const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
+                       int64_t K, const float* bias, int flags) {
+  using C = Cfg<CG>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  if (make_map(&ma_hi, a_hi, M, K, lda, ROWS_A)) return 1;
+  if (make_map(&ma_lo, a_lo, M, K, lda, ROWS_A)) return 1;
+  if (make_map(&mb_hi, b_hi, N, K, ldb, C::ROWS_B)) return 1;
+  if (make_map(&mb_lo, b_lo, N, K, ldb, C::ROWS_B)) return 1;
+  auto kern = gemm_tf32x3_kernel<CG>;
+  if (!g_attr_set[CG]) {
+    TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    g_attr_set[CG] = true;
+  }
+  const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
+  int groups = (int)std::min<int64_t>(tiles, ctx().sm_count / CG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = ctx().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_begin(1);
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags));
+  ctx().launches++;
+  prof_end(1);
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace tnn
+
+using namespace tnn;
+
+extern "C" {
+
+int tnn_split_tf32(const float* x, int64_t R, int64_t C, float* hi, float* lo, int64_t ldp,
+                   float* hiT, float* loT, int64_t ldt) {
+  TNN_REQUIRE_INIT();
+  if (R <= 0 || C <= 0) return 0;
+  if ((hi == nullptr) != (lo == nullptr) || (hiT == nullptr) != (loT == nullptr))
+    TNN_FAIL("tnn_split_tf32: hi/lo planes come in pairs");
+  if (hi && (ldp % 4 != 0 || ldp < C)) TNN_FAIL("tnn_split_tf32: ldp must be >= C and a multiple of 4");
+  if (hiT && (ldt % 4 != 0 || ldt < R)) TNN_FAIL("tnn_split_tf32: ldt must be >= R and a multiple of 4");
+  dim3 grid((unsigned)ceil_div(C, 64), (unsigned)ceil_div(R, 64));
+  if (grid.y > 65535) TNN_FAIL("tnn_split_tf32: more than 65535*64 rows");
+  int vec_in = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  prof_begin(3);
+  tc::split_tf32_kernel<<<grid, 256, 0, ctx().stream>>>(x, R, C, hi, lo, ldp, hiT, loT, ldt, vec_in);
+  TNN_POST_LAUNCH();
+  prof_end(3);
+  return 0;
+}
+
+int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
+                    const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
+                    int64_t K, const float* bias, int flags) {
+  TNN_REQUIRE_INIT();
+  if (M <= 0 || N <= 0) return 0;
+  if (K <= 0) TNN_FAIL("tnn_gemm_tf32x3: K must be positive");
+  if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) TNN_FAIL("tnn_gemm_tf32x3: extent above int32");
+  if (tc::get_encode_fn()) return 1;
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("TNN_GEMM_CG");
+    if (e) tc::g_force_cg = atoi(e);
+    env_read = true;
+  }
+  int cg = tc::g_force_cg ? tc::g_force_cg : 1;
+  if (cg == 2)
+    return tc::launch_gemm<2>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+  return tc::launch_gemm<1>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+}
+
+}  // extern "C"

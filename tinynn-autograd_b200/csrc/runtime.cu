@@ -1,0 +1,396 @@
+// Runtime plumbing of libtnn_b200: device context, the stream-ordered caching pool that stands
+// in for numpy's implicit malloc/free (every ops.py call allocates its result), host<->device
+// copies, events and per-kernel-family profiling.
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tnn {
+
+static Context g_ctx;
+static thread_local std::string g_err;
+static std::string g_err_shared;
+
+Context& ctx() { return g_ctx; }
+
+void set_error(const std::string& msg) {
+  g_err = msg;
+  g_err_shared = msg;
+}
+
+int fail(const char* file, int line, const std::string& msg) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), ":%d: ", line);
+  const char* base = file;
+  for (const char* p = file; *p; ++p)
+    if (*p == '/') base = p + 1;
+  set_error(std::string(base) + buf + msg);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Caching pool.  All device work is queued on one compute stream, so a block released by the
+// host can be handed to a later launch without an event: stream order already guarantees the
+// earlier kernels that touched it have run.  (The copy stream only ever writes into buffers the
+// host has fenced with tnn_copy_wait_compute.)
+// ------------------------------------------------------------------------------------------
+struct Pool {
+  std::mutex mu;
+  std::unordered_map<size_t, std::vector<void*>> free_lists;  // rounded size -> blocks
+  std::unordered_map<void*, size_t> live;                     // block -> rounded size
+  std::unordered_map<void*, size_t> owned;                    // every cudaMalloc'd block
+  size_t reserved = 0, in_use = 0, n_malloc = 0;
+};
+static Pool g_pool;
+
+static size_t round_size(size_t n) {
+  if (n == 0) n = 1;
+  if (n <= (1u << 20)) return (n + 511) & ~size_t(511);
+  const size_t g = size_t(2) << 20;
+  return (n + g - 1) / g * g;
+}
+
+static void pool_release_all_free_locked() {
+  for (auto& kv : g_pool.free_lists) {
+    for (void* p : kv.second) {
+      cudaFree(p);
+      g_pool.reserved -= kv.first;
+      g_pool.owned.erase(p);
+    }
+    kv.second.clear();
+  }
+}
+
+int get_scratch(size_t nbytes, void** out) {
+  Context& c = ctx();
+  if (nbytes > c.scratch_bytes) {
+    // the old scratch may still be read by queued kernels: drain before replacing it
+    if (c.scratch) {
+      TNN_CUDA(cudaStreamSynchronize(c.stream));
+      TNN_CUDA(cudaFree(c.scratch));
+      c.scratch = nullptr;
+      c.scratch_bytes = 0;
+    }
+    size_t want = nbytes < (size_t(1) << 20) ? (size_t(1) << 20) : nbytes * 2;
+    TNN_CUDA(cudaMalloc(&c.scratch, want));
+    c.scratch_bytes = want;
+  }
+  *out = c.scratch;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------
+struct ProfPair {
+  cudaEvent_t a, b;
+};
+static std::vector<ProfPair> g_prof_used;
+static std::vector<ProfPair> g_prof_free;
+static ProfPair g_prof_cur;
+
+void prof_begin(int family) {
+  Context& c = ctx();
+  if (c.prof_family != family) return;
+  if (g_prof_free.empty()) {
+    ProfPair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    g_prof_free.push_back(p);
+  }
+  g_prof_cur = g_prof_free.back();
+  g_prof_free.pop_back();
+  cudaEventRecord(g_prof_cur.a, c.stream);
+}
+
+void prof_end(int family) {
+  Context& c = ctx();
+  if (c.prof_family != family) return;
+  cudaEventRecord(g_prof_cur.b, c.stream);
+  g_prof_used.push_back(g_prof_cur);
+}
+
+}  // namespace tnn
+
+using namespace tnn;
+
+extern "C" {
+
+const char* tnn_last_error(void) { return g_err_shared.c_str(); }
+
+int tnn_device_count(int* n) {
+  TNN_CUDA(cudaGetDeviceCount(n));
+  return 0;
+}
+
+int tnn_init(int device) {
+  Context& c = ctx();
+  if (c.inited) {
+    if (c.device == device) return 0;
+    TNN_FAIL("tnn_init: already initialised on another device");
+  }
+  TNN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TNN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    TNN_FAIL(std::string("libtnn_b200 is built for sm_100a only; device is ") + prop.name);
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  c.l2_bytes = (size_t)prop.l2CacheSize;
+  TNN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  TNN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  TNN_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+  TNN_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
+  c.inited = true;
+  return 0;
+}
+
+int tnn_shutdown(void) {
+  Context& c = ctx();
+  if (!c.inited) return 0;
+  cudaStreamSynchronize(c.stream);
+  cudaStreamSynchronize(c.copy_stream);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    for (auto& kv : g_pool.owned) cudaFree(kv.first);
+    g_pool.owned.clear();
+    g_pool.live.clear();
+    g_pool.free_lists.clear();
+    g_pool.reserved = g_pool.in_use = 0;
+  }
+  if (c.scratch) cudaFree(c.scratch);
+  if (c.l2_flush_buf) cudaFree(c.l2_flush_buf);
+  c.scratch = c.l2_flush_buf = nullptr;
+  c.scratch_bytes = c.l2_flush_bytes = 0;
+  cudaEventDestroy(c.ev_copy);
+  cudaEventDestroy(c.ev_compute);
+  cudaStreamDestroy(c.stream);
+  cudaStreamDestroy(c.copy_stream);
+  c.inited = false;
+  return 0;
+}
+
+int tnn_sync(void) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int tnn_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem,
+                    size_t* l2_bytes) {
+  TNN_REQUIRE_INIT();
+  cudaDeviceProp prop;
+  TNN_CUDA(cudaGetDeviceProperties(&prop, ctx().device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
+  return 0;
+}
+
+void* tnn_stream(void) { return (void*)ctx().stream; }
+uint64_t tnn_launch_count(void) { return ctx().launches; }
+
+// ---- pool ----------------------------------------------------------------------------------
+int tnn_alloc(size_t nbytes, void** out) {
+  TNN_REQUIRE_INIT();
+  size_t r = round_size(nbytes);
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  auto it = g_pool.free_lists.find(r);
+  void* p = nullptr;
+  if (it != g_pool.free_lists.end() && !it->second.empty()) {
+    p = it->second.back();
+    it->second.pop_back();
+  } else {
+    cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess) {
+      // out of memory: drop every cached block (after draining the stream) and retry once
+      cudaGetLastError();
+      cudaStreamSynchronize(ctx().stream);
+      pool_release_all_free_locked();
+      e = cudaMalloc(&p, r);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        TNN_FAIL(std::string("tnn_alloc: cudaMalloc(") + std::to_string(r) +
+                 ") failed: " + cudaGetErrorString(e));
+      }
+    }
+    g_pool.owned[p] = r;
+    g_pool.reserved += r;
+    g_pool.n_malloc++;
+  }
+  g_pool.live[p] = r;
+  g_pool.in_use += r;
+  *out = p;
+  return 0;
+}
+
+int tnn_free(void* p) {
+  if (!p) return 0;
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  auto it = g_pool.live.find(p);
+  if (it == g_pool.live.end()) {
+    if (!ctx().inited) return 0;  // after shutdown everything is already gone
+    TNN_FAIL("tnn_free: pointer was not allocated by tnn_alloc (or double free)");
+  }
+  size_t r = it->second;
+  g_pool.live.erase(it);
+  g_pool.in_use -= r;
+  g_pool.free_lists[r].push_back(p);
+  return 0;
+}
+
+int tnn_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* n_cuda_malloc) {
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  if (reserved_bytes) *reserved_bytes = g_pool.reserved;
+  if (in_use_bytes) *in_use_bytes = g_pool.in_use;
+  if (n_cuda_malloc) *n_cuda_malloc = g_pool.n_malloc;
+  return 0;
+}
+
+int tnn_pool_trim(void) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaStreamSynchronize(ctx().stream));
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  pool_release_all_free_locked();
+  return 0;
+}
+
+// ---- copies --------------------------------------------------------------------------------
+int tnn_h2d(void* dst, const void* src, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  if (nbytes == 0) return 0;
+  TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
+int tnn_d2h(void* dst, const void* src, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  if (nbytes == 0) return 0;
+  TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
+  TNN_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int tnn_d2d(void* dst, const void* src, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  if (nbytes == 0) return 0;
+  TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx().stream));
+  return 0;
+}
+
+int tnn_memset(void* dst, int byte, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  if (nbytes == 0) return 0;
+  TNN_CUDA(cudaMemsetAsync(dst, byte, nbytes, ctx().stream));
+  return 0;
+}
+
+int tnn_host_alloc(size_t nbytes, void** out) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaHostAlloc(out, nbytes ? nbytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int tnn_host_free(void* p) {
+  if (!p) return 0;
+  TNN_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int tnn_h2d_async_copy_stream(void* dst, const void* pinned_src, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  if (nbytes == 0) return 0;
+  TNN_CUDA(cudaMemcpyAsync(dst, pinned_src, nbytes, cudaMemcpyHostToDevice, ctx().copy_stream));
+  return 0;
+}
+
+int tnn_copy_wait_compute(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  TNN_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+  TNN_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_compute, 0));
+  return 0;
+}
+
+int tnn_compute_wait_copy(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  TNN_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+  TNN_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+  return 0;
+}
+
+// ---- events --------------------------------------------------------------------------------
+int tnn_event_create(void** ev) {
+  TNN_REQUIRE_INIT();
+  cudaEvent_t e;
+  TNN_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return 0;
+}
+
+int tnn_event_destroy(void* ev) {
+  if (ev) TNN_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+
+int tnn_event_record(void* ev) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx().stream));
+  return 0;
+}
+
+int tnn_event_elapsed_ms(void* start, void* stop, float* ms) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  TNN_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+
+int tnn_prof_enable(int family) {
+  TNN_REQUIRE_INIT();
+  ctx().prof_family = family;
+  return 0;
+}
+
+int tnn_prof_collect(double* total_ms, uint64_t* n_launches) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaStreamSynchronize(ctx().stream));
+  double tot = 0.0;
+  for (auto& p : g_prof_used) {
+    float ms = 0.f;
+    TNN_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+    tot += ms;
+    g_prof_free.push_back(p);
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = g_prof_used.size();
+  g_prof_used.clear();
+  return 0;
+}
+
+__global__ void l2_flush_kernel(float4* buf, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int tnn_l2_flush(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  if (!c.l2_flush_buf) {
+    size_t want = c.l2_bytes ? c.l2_bytes * 2 : (size_t(256) << 20);
+    TNN_CUDA(cudaMalloc(&c.l2_flush_buf, want));
+    c.l2_flush_bytes = want;
+  }
+  size_t n4 = c.l2_flush_bytes / sizeof(float4);
+  l2_flush_kernel<<<c.sm_count * 8, 256, 0, c.stream>>>((float4*)c.l2_flush_buf, n4);
+  TNN_POST_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"
