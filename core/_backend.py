@@ -87,6 +87,7 @@ _SIGNATURES = {
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                         _c_i64, _c_vp, _c_int],
+    "tnn_set_gemm_cta_group": [_c_int],
     "tnn_relu_fwd": [_c_int, _c_vp, _c_vp, _c_i64],
     "tnn_relu_bwd": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_colsum": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
@@ -602,6 +603,12 @@ def split_planes(x, transposed, also_other=False):
     if want_t:
         cache["t"] = (hit, lot, ldt)
     return cache[key]
+
+
+def set_gemm_cta_group(cg):
+    load_library()
+    if _lib.tnn_set_gemm_cta_group(int(cg)):
+        _raise("tnn_set_gemm_cta_group")
 
 
 def use_tensor_cores(M, N, K, dtype):

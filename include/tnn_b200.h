@@ -166,6 +166,10 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd,
                     const float* b_hi, const float* b_lo, int64_t ldb,
                     int64_t M, int64_t N, int64_t K, const float* bias, int flags);
 
+/* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
+ * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
+int tnn_set_gemm_cta_group(int cg);
+
 /* ---- fused layer ops ----------------------------------------------------------------------- */
 /* ReLU = clip(x, 0.0) (layers.py:97-98); backward mask is x >= 0 (ops.py:336-343) */
 int tnn_relu_fwd(int dtype, void* out, const void* x, int64_t n);

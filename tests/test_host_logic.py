@@ -1,0 +1,203 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/tnn_b200.h declares,
+host-side shape/stride/shard logic, the double-double exp/log (compiled for the host from the
+same header the kernels use), and the host utilities that mirror the reference's utils/."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
+    import core._backend as be
+    return be
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    be = built_lib
+    header = open(os.path.join(ROOT, "include", "tnn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(tnn_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) > 50
+    lib = ctypes.CDLL(be.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # the ctypes binding types every one of them
+    assert declared == set(be.EXPORTED_SYMBOLS), declared ^ set(be.EXPORTED_SYMBOLS)
+    be.load_library()
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    """on a box without a GPU the first device operation fails loudly"""
+    be = built_lib
+    n = ctypes.c_int(0)
+    lib = be.load_library()
+    has_gpu = lib.tnn_device_count(ctypes.byref(n)) == 0 and n.value > 0
+    if has_gpu:
+        pytest.skip("GPU present")
+    from core.tensor import Tensor
+    with pytest.raises(be.BackendError):
+        Tensor([1.0, 2.0])
+
+
+def test_product_path_does_not_import_oracle():
+    for sub in ("core", "utils", "tinynn-autograd_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "ref_numpy" not in src and "import oracle" not in src, f
+
+
+def test_shape_and_stride_helpers(built_lib):
+    be = built_lib
+    import core.ops as ops
+    assert ops._resolve_shape(24, (3, -1)) == (3, 8)
+    assert ops._resolve_shape(24, 24) == (24,)
+    with pytest.raises(ValueError):
+        ops._resolve_shape(24, (5, -1))
+    with pytest.raises(ValueError):
+        ops._resolve_shape(24, (-1, -1))
+    assert be._bstrides((5,), (6, 5)) == [0, 1]
+    assert be._bstrides((1, 5), (6, 5)) == [0, 1]
+    assert be._bstrides((6, 1), (6, 5)) == [1, 0]
+    assert be._bstrides((), (6, 5)) == [0, 0]
+    assert be._bstrides((3, 1), (2, 3, 4)) == [0, 1, 0]
+    assert be._cstrides((2, 3, 4)) == [12, 4, 1]
+    assert be.device_dtype(np.int64) == np.float64 and be.device_dtype(np.float32) == np.float32
+    assert be._round4(70) == 72
+
+
+def test_shard_bounds_and_stats_merge():
+    import core._dist as dist
+    for n, w in ((65536, 8), (10, 3), (7, 8)):
+        cuts = [dist.shard_bounds(n, r, w) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1
+    rng = np.random.RandomState(0)
+    z = rng.standard_normal((64, 10)) * 5
+    parts = np.array_split(z, 4)
+    pairs = [(p.max(), np.exp(p - p.max()).sum()) for p in parts]
+    m, s = dist.merge_stats_host(pairs)
+    assert m == z.max() and abs(s - np.exp(z - z.max()).sum()) <= 1e-12 * s
+
+
+def test_exp_log_double_double_on_host(tmp_path):
+    """math.cuh's exp_cr/log_cr (the float64 device path) compiled with g++: correctly rounded on
+    the reference's known-answer inputs and on a random sweep (vs mpmath when available)"""
+    src = tmp_path / "m.cpp"
+    src.write_text('#include "math.cuh"\n'
+                   'extern "C" void exp_arr(const double* x, double* y, int n){for(int i=0;i<n;i++)y[i]=tnn::exp_cr(x[i]);}\n'
+                   'extern "C" void log_arr(const double* x, double* y, int n){for(int i=0;i<n;i++)y[i]=tnn::log_cr(x[i]);}\n')
+    so = tmp_path / "libm_test.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
+                           "-I", os.path.join(ROOT, "tinynn-autograd_b200", "csrc"), str(src), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+
+    def run(fn, x):
+        y = np.empty_like(x)
+        fn(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), len(x))
+        return y
+    k = np.array([1.0, 3.0, 5.0])
+    assert [v.hex() for v in run(lib.exp_arr, k)] == [
+        "0x1.5bf0a8b145769p+1", "0x1.415e5bf6fb106p+4", "0x1.28d389970338fp+7"]
+    assert [v.hex() for v in run(lib.log_arr, k)] == [
+        "0x0.0p+0", "0x1.193ea7aad030bp+0", "0x1.9c041f7ed8d33p+0"]
+    rng = np.random.RandomState(0)
+    x = rng.uniform(-40, 40, 2000)
+    e = run(lib.exp_arr, x)
+    assert np.max(np.abs(e - np.exp(x)) / np.spacing(np.exp(x))) <= 1.0
+    try:
+        import mpmath
+    except ImportError:
+        return
+    mpmath.mp.prec = 200
+    cr = np.array([float(mpmath.exp(mpmath.mpf(float(v)))) for v in x[:500]])
+    assert np.array_equal(e[:500], cr)
+    y = np.exp(rng.uniform(-60, 60, 500))
+    crl = np.array([float(mpmath.log(mpmath.mpf(float(v)))) for v in y])
+    assert np.array_equal(run(lib.log_arr, y), crl)
+
+
+# ---- host utilities mirrored from the reference's utils/ and core/initializer.py ---------------
+def test_initializers_statistics():
+    import core.initializer as I
+    shape, tol = (100000, 1), 1e-2
+    assert I.get_fans((100, 10)) == (100, 10)
+    fi, fo = I.get_fans((64, 5, 5, 128))
+    assert fi == 5 * 5 * 128 and fo == 64
+    v = I.NormalInit(0.0, 1.0).init(shape)
+    assert abs(v.mean()) <= tol and abs(v.std() - 1.0) <= tol
+    v = I.TruncatedNormalInit(0.0, 1.0).init(shape)
+    assert abs(v.mean()) <= tol and v.min() >= -2.0 and v.max() <= 2.0
+    v = I.UniformInit(-1.0, 1.0).init(shape)
+    assert v.min() >= -1.0 and v.max() <= 1.0
+    assert np.all(I.ConstantInit(3.1).init(shape) == 3.1)
+    b = np.sqrt(6.0 / np.sum(I.get_fans(shape)))
+    v = I.XavierUniformInit().init(shape)
+    assert v.min() >= -b and v.max() <= b
+    s = np.sqrt(2.0 / np.sum(I.get_fans(shape)))
+    assert abs(I.XavierNormalInit().init(shape).std() - s) <= tol
+    b = np.sqrt(6.0 / I.get_fans(shape)[0])
+    v = I.HeUniformInit().init(shape)
+    assert v.min() >= -b and v.max() <= b
+    s = np.sqrt(2.0 / I.get_fans(shape)[0])
+    assert abs(I.HeNormalInit().init(shape).std() - s) <= tol
+    # same RNG stream as the reference: Xavier draws are np.random.uniform(-a, a, shape)
+    np.random.seed(0)
+    a = I.XavierUniformInit().init([784, 200])
+    np.random.seed(0)
+    bound = np.sqrt(6.0 / 984)
+    assert np.array_equal(a, np.random.uniform(low=-bound, high=bound, size=[784, 200]))
+
+
+def test_batch_iterator_on_arrays():
+    from utils.data_iterator import BatchIterator
+    x = np.random.randint(0, 100, size=(100, 10))
+    y = np.random.randint(0, 100, size=(100, 5))
+    n = 0
+    for bx, by in BatchIterator(batch_size=10)(x, y):
+        assert bx.shape == (10, 10) and by.shape == (10, 5)
+        n += 1
+    assert n == 10
+    # ragged tail (50000 = 390*128 + 80 in run.py) and the shuffle's RNG call
+    sizes = [len(b.inputs) for b in BatchIterator(batch_size=128, shuffle=False)(np.zeros((1000, 2)), np.zeros((1000, 1)))]
+    assert sizes == [128] * 7 + [104]
+    np.random.seed(3)
+    first = next(iter(BatchIterator(batch_size=4)(np.arange(20), np.arange(20)))).inputs
+    np.random.seed(3)
+    idx = np.arange(20)
+    np.random.shuffle(idx)
+    assert first.tolist() == idx[:4].tolist()
+
+
+def test_seeder_and_timer():
+    from utils.seeder import random_seed
+    from utils.timer import Timer
+    with pytest.raises(ValueError):
+        random_seed(2 ** 32)
+    random_seed(1)
+    a = np.random.rand()
+    random_seed(1)
+    assert a == np.random.rand()
+    t = Timer("t")
+    t.start()
+    time.sleep(0.05)
+    t.pause()
+    time.sleep(0.02)
+    t.start()
+    time.sleep(0.05)
+    t.stop()
+    assert t.count == 2 and 0.1 <= t.duration <= 0.2

@@ -73,13 +73,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
 // bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+  long long t0 = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
+    if (spin == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) break;   // ~2 s at 1.9 GHz
   }
   printf("tnn gemm_tc: mbarrier wait timed out (block %d thread %d bar %x parity %u)\n",
          (int)blockIdx.x, (int)threadIdx.x, bar, parity);
@@ -509,7 +513,8 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
   return 0;
 }
 
-static int g_force_cg = 0;  // 0 = auto, 1 / 2 = forced (TNN_GEMM_CG)
+constexpr int DEFAULT_CG = 1;
+static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3] = {false, false, false};
 
 template <int CG>
@@ -573,6 +578,12 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C, float* hi, float* lo, i
   return 0;
 }
 
+int tnn_set_gemm_cta_group(int cg) {
+  if (cg != 0 && cg != 1 && cg != 2) TNN_FAIL("tnn_set_gemm_cta_group: 0 (default), 1 or 2");
+  tc::g_force_cg = cg;
+  return 0;
+}
+
 int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
                     int64_t K, const float* bias, int flags) {
@@ -584,10 +595,10 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
   static bool env_read = false;
   if (!env_read) {
     const char* e = getenv("TNN_GEMM_CG");
-    if (e) tc::g_force_cg = atoi(e);
+    if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
     env_read = true;
   }
-  int cg = tc::g_force_cg ? tc::g_force_cg : 1;
+  int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
   if (cg == 2)
     return tc::launch_gemm<2>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
   return tc::launch_gemm<1>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
