@@ -268,7 +268,7 @@ def empty(shape, dtype):
 def from_numpy(arr, dtype=None):
     arr = np.asarray(arr)
     dt = device_dtype(arr.dtype if dtype is None else dtype)
-    host = np.ascontiguousarray(arr, dtype=dt)
+    host = np.require(arr, dtype=dt, requirements="C")  # (ascontiguousarray would make 0-d 1-d)
     out = empty(host.shape, dt)
     if host.size:
         if _lib.tnn_h2d(out.ptr, host.ctypes.data, host.nbytes):

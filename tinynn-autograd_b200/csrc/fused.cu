@@ -266,19 +266,20 @@ opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH h
     if constexpr (OPT == TNN_OPT_SGD) {
       step = -(T)hh.h[0] * g;
     } else if constexpr (OPT == TNN_OPT_ADAM) {
-      const T lr = (T)hh.h[0], b1 = (T)hh.h[1], b2 = (T)hh.h[2], eps = (T)hh.h[3];
+      // 1-b1 and 1-b2 are formed in double like the reference's Python floats, then narrowed
+      const T lr = (T)hh.h[0], omb1 = (T)(1.0 - hh.h[1]), omb2 = (T)(1.0 - hh.h[2]), eps = (T)hh.h[3];
       const T bc1 = (T)hh.h[4], bc2 = (T)hh.h[5];
       T m = s0[i], v = s1[i];
-      m += (T(1) - b1) * (g - m);
-      v += (T(1) - b2) * (g * g - v);
+      m += omb1 * (g - m);
+      v += omb2 * (g * g - v);
       s0[i] = m;
       s1[i] = v;
       T mh = m / bc1, vh = v / bc2;
       step = -lr * mh / (m_sqrt(vh) + eps);
     } else if constexpr (OPT == TNN_OPT_RMSPROP) {
-      const T lr = (T)hh.h[0], decay = (T)hh.h[1], mom_c = (T)hh.h[2], eps = (T)hh.h[3];
+      const T lr = (T)hh.h[0], omd = (T)(1.0 - hh.h[1]), mom_c = (T)hh.h[2], eps = (T)hh.h[3];
       T ms = s0[i], mom = s1[i];
-      ms += (T(1) - decay) * (g * g - ms);
+      ms += omd * (g * g - ms);
       mom = mom_c * mom + lr * g / m_sqrt(ms + eps);
       s0[i] = ms;
       s1[i] = mom;
@@ -294,13 +295,13 @@ opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH h
       s0[i] = G;
       step = -(lr / m_sqrt(G + eps)) * g;
     } else {  // ADADELTA
-      const T lr = (T)hh.h[0], decay = (T)hh.h[1], eps = (T)hh.h[2];
+      const T lr = (T)hh.h[0], omd = (T)(1.0 - hh.h[1]), eps = (T)hh.h[2];
       T Eg = s0[i], delta = s1[i];
-      Eg += (T(1) - decay) * (g * g - Eg);
+      Eg += omd * (g * g - Eg);
       T sd = m_sqrt(delta + eps);
       T d = g * (sd / m_sqrt(Eg + eps));
       step = -lr * d;
-      delta += (T(1) - decay) * (d * d - delta);
+      delta += omd * (d * d - delta);
       s0[i] = Eg;
       s1[i] = delta;
     }
@@ -316,7 +317,7 @@ adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh) {
   using VT = typename V4<T>::type;
   using U = typename V4<T>::U;
   constexpr int W = V4<T>::W;
-  const T lr = (T)hh.h[0], b1 = (T)hh.h[1], b2 = (T)hh.h[2], eps = (T)hh.h[3];
+  const T lr = (T)hh.h[0], omb1 = (T)(1.0 - hh.h[1]), omb2 = (T)(1.0 - hh.h[2]), eps = (T)hh.h[3];
   const T bc1 = (T)hh.h[4], bc2 = (T)hh.h[5];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
@@ -327,8 +328,8 @@ adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh) {
     p.v = reinterpret_cast<const VT*>(param)[i];
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      m.e[k] += (T(1) - b1) * (g.e[k] - m.e[k]);
-      v.e[k] += (T(1) - b2) * (g.e[k] * g.e[k] - v.e[k]);
+      m.e[k] += omb1 * (g.e[k] - m.e[k]);
+      v.e[k] += omb2 * (g.e[k] * g.e[k] - v.e[k]);
       T mh = m.e[k] / bc1, vh = v.e[k] / bc2;
       p.e[k] += -lr * mh / (m_sqrt(vh) + eps);
     }

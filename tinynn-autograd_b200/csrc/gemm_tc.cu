@@ -10,9 +10,14 @@
 //   tnn_gemm_tf32x3  D[M,N] = A[M,K] * B[N,K]^T.  Persistent, warp-specialised:
 //                      warp 0    TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier tx)
 //                      warp 1    MMA issuer    (tcgen05.mma.kind::tf32, 3 MMAs per K=8 step)
-//                      warps 2-5 epilogue      (tcgen05.ld TMEM -> regs -> +bias/relu/accumulate)
-//                    Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue
-//                    of tile i overlaps the main loop of tile i+1.
+//                      warps 2-9 epilogue      (tcgen05.ld TMEM -> fp32 regs (+=) -> bias/relu/accumulate)
+//                    The tensor core accumulates in fp32 with round-toward-zero, which biases a long
+//                    K loop (measured: ~6e-5 relative at K = 4096).  So a TMEM accumulator only
+//                    ever holds a short chain (CHUNK_KB K blocks = 128 k): the 8 epilogue warps
+//                    drain each chunk with tcgen05.ld and add it, round-to-nearest, into fp32
+//                    registers (128 per thread) that carry the tile.  The two TMEM accumulators
+//                    (2 x 256 columns) alternate per chunk, so draining chunk c overlaps the MMAs
+//                    of chunk c+1 and the store of tile i overlaps the first chunks of tile i+1.
 //                    CG = 1: one CTA per SM, tile 128 x 256.
 //                    CG = 2: CTA pair (cta_group::2), tile 256 x 256, each CTA stages its own
 //                            128 rows of A and half of B -> half the L2->SMEM operand traffic
@@ -34,7 +39,8 @@ constexpr int ROWS_A = 128;               // A rows staged per CTA
 constexpr int UMMA_N = 256;               // accumulator columns per tile
 constexpr int UMMA_K = 8;                 // tf32
 constexpr int PLANE_ROW_BYTES = BK * 4;   // 128
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
+constexpr int CHUNK_KB = 4;               // K blocks accumulated inside the tensor core per chunk
 constexpr uint32_t TMEM_COLS = 512;
 
 template <int CG>
@@ -240,7 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp of every CTA in the group
+      mbar_init(tempty_bar(a), 8 * CG);  // one arrival per epilogue warp of every CTA in the group
     }
     fence_barrier_init();
   }
@@ -298,105 +304,115 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = group; t < num_tiles; t += num_groups) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sa_lo = sa_hi + C::A_BYTES;
-          const uint32_t sb_hi = sa_lo + C::A_BYTES;
-          const uint32_t sb_lo = sb_hi + C::B_BYTES;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
+          const int kb1 = min(kb0 + CHUNK_KB, num_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sa_lo = sa_hi + C::A_BYTES;
+            const uint32_t sb_hi = sa_lo + C::A_BYTES;
+            const uint32_t sb_lo = sb_hi + C::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = (uint32_t)(k * UMMA_K * 4);  // bytes inside the 128-byte row
-            const uint64_t da_hi = make_smem_desc(sa_hi + koff);
-            const uint64_t da_lo = make_smem_desc(sa_lo + koff);
-            const uint64_t db_hi = make_smem_desc(sb_hi + koff);
-            const uint64_t db_lo = make_smem_desc(sb_lo + koff);
-            // small terms first
-            umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
-            umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = (uint32_t)(k * UMMA_K * 4);  // bytes inside the 128-byte row
+              const uint64_t da_hi = make_smem_desc(sa_hi + koff);
+              const uint64_t da_lo = make_smem_desc(sa_lo + koff);
+              const uint64_t db_hi = make_smem_desc(sb_hi + koff);
+              const uint64_t db_lo = make_smem_desc(sb_lo + koff);
+              // small terms first; the first MMA of a chunk overwrites the accumulator
+              umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
+            }
+            umma_commit<CG>(empty_bar(stage));          // frees the smem slot when the MMAs retire
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          umma_commit<CG>(empty_bar(stage));          // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1u;
+          umma_commit<CG>(tfull_bar(acc));              // chunk complete -> epilogue may drain it
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
           }
-        }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
         }
       }
     }
   } else {
-    // ================= epilogue: TMEM -> registers -> global =================
+    // ================= epilogue: TMEM chunks -> fp32 registers (RN adds) -> global =================
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;                // accumulator columns [128*half, 128*half+128)
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool accumulate = flags & 1, relu = flags & 2;
     for (int t = group; t < num_tiles; t += num_groups) {
       const int tm = t / tiles_n, tn = t % tiles_n;
       const int row = tm * C::TILE_M + (int)cta_rank * ROWS_A + quad * 32 + lane;
-      const int col0 = tn * UMMA_N;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * UMMA_N);
-      float* drow = D + (int64_t)row * ldd;
-#pragma unroll 1
-      for (int c = 0; c < UMMA_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int col = col0 + c;
-        if (row < M && col < N) {
-          if (col + 32 <= N && ((reinterpret_cast<uintptr_t>(drow + col) & 15) == 0)) {
+      const int col0 = tn * UMMA_N + half * 128;
+      float sum[128];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-              if (bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + col + j);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              if (accumulate) {
-                const float4 o = *reinterpret_cast<const float4*>(drow + col + j);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              if (relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-                v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(drow + col + j) = v;
+      for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                               (uint32_t)(acc * UMMA_N + half * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        // this warp is done reading the accumulator: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(tempty_bar(acc), 0);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if (row < M && col0 < N) {
+        float* drow = D + (int64_t)row * ldd;
+        if (col0 + 128 <= N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 128; j += 4) {
+            float4 v = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+            if (bias) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
-          } else {
+            if (accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(drow + col0 + j);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            if (relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+              v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(drow + col0 + j) = v;
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col + j < N) {
-                float v = __uint_as_float(r[j]);
-                if (bias) v += bias[col + j];
-                if (accumulate) v += drow[col + j];
-                if (relu) v = fmaxf(v, 0.f);
-                drow[col + j] = v;
-              }
+          for (int j = 0; j < 128; ++j) {
+            if (col0 + j < N) {
+              float v = sum[j];
+              if (bias) v += bias[col0 + j];
+              if (accumulate) v += drow[col0 + j];
+              if (relu) v = fmaxf(v, 0.f);
+              drow[col0 + j] = v;
             }
           }
         }
-      }
-      // this warp is done reading the accumulator: hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(tempty_bar(acc), 0);
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
   }
