@@ -529,7 +529,7 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
   return 0;
 }
 
-constexpr int DEFAULT_CG = 1;
+constexpr int DEFAULT_CG = 2;  // CTA pairs: measured 0.98 ms vs 1.10 ms per 8192x4096x4096 product
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3] = {false, false, false};
 

@@ -97,60 +97,75 @@ reduce_row_warp_kernel(T* out, const T* x, int64_t outer, int64_t red) {
   }
 }
 
-// ---- inner > 1: threads along the contiguous inner axis, walk down the reduced axis ------------
+// ---- inner > 1: a CTA owns 32 column slots (128-bit each when vectorised) x a chunk of rows ------
+// thread (tx, ty) of the 32 x 8 block walks rows lo+ty, lo+ty+8, ... of its column slot (coalesced
+// across tx), the 8 row lanes are folded through shared memory in fixed order.
 template <int RED, typename T, int VEC>
 __global__ void __launch_bounds__(256)
 reduce_col_kernel(T* out, const T* x, int64_t red, int64_t inner, int nsplit) {
+  __shared__ T sm[8][32 * VEC + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t ncol = inner / VEC;
-  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= ncol) return;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
   const int64_t o = blockIdx.y / nsplit;
   const int s = blockIdx.y % nsplit;
   const int64_t chunk = ceil_div(red, nsplit);
   const int64_t lo = (int64_t)s * chunk;
   int64_t hi = lo + chunk;
   if (hi > red) hi = red;
-  const T* base = x + (o * red) * inner + col * VEC;
   T acc[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = red_identity<RED, T>();
-  if constexpr (VEC == 1) {
-    int64_t r = lo;
-    for (; r + 3 < hi; r += 4) {
-      T v0 = base[r * inner], v1 = base[(r + 1) * inner], v2 = base[(r + 2) * inner],
-        v3 = base[(r + 3) * inner];
-      acc[0] = red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[0], v0), v1), v2), v3);
-    }
-    for (; r < hi; ++r) acc[0] = red_op<RED, T>(acc[0], base[r * inner]);
-  } else {
-    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-    union U {
-      V v;
-      T e[VEC];
-    };
-    int64_t r = lo;
-    for (; r + 3 < hi; r += 4) {
-      U u0, u1, u2, u3;
-      u0.v = *reinterpret_cast<const V*>(base + r * inner);
-      u1.v = *reinterpret_cast<const V*>(base + (r + 1) * inner);
-      u2.v = *reinterpret_cast<const V*>(base + (r + 2) * inner);
-      u3.v = *reinterpret_cast<const V*>(base + (r + 3) * inner);
+  if (col < ncol) {
+    const T* base = x + (o * red) * inner + col * VEC;
+    if constexpr (VEC == 1) {
+      int64_t r = lo + ty;
+      for (; r + 24 < hi; r += 32) {
+        T v0 = base[r * inner], v1 = base[(r + 8) * inner], v2 = base[(r + 16) * inner],
+          v3 = base[(r + 24) * inner];
+        acc[0] = red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[0], v0), v1), v2), v3);
+      }
+      for (; r < hi; r += 8) acc[0] = red_op<RED, T>(acc[0], base[r * inner]);
+    } else {
+      using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+      union U {
+        V v;
+        T e[VEC];
+      };
+      int64_t r = lo + ty;
+      for (; r + 24 < hi; r += 32) {
+        U u0, u1, u2, u3;
+        u0.v = *reinterpret_cast<const V*>(base + r * inner);
+        u1.v = *reinterpret_cast<const V*>(base + (r + 8) * inner);
+        u2.v = *reinterpret_cast<const V*>(base + (r + 16) * inner);
+        u3.v = *reinterpret_cast<const V*>(base + (r + 24) * inner);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        acc[k] = red_op<RED, T>(
-            red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[k], u0.e[k]), u1.e[k]), u2.e[k]),
-            u3.e[k]);
-    }
-    for (; r < hi; ++r) {
-      U u;
-      u.v = *reinterpret_cast<const V*>(base + r * inner);
+        for (int k = 0; k < VEC; ++k)
+          acc[k] = red_op<RED, T>(
+              red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[k], u0.e[k]), u1.e[k]), u2.e[k]),
+              u3.e[k]);
+      }
+      for (; r < hi; r += 8) {
+        U u;
+        u.v = *reinterpret_cast<const V*>(base + r * inner);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = red_op<RED, T>(acc[k], u.e[k]);
+        for (int k = 0; k < VEC; ++k) acc[k] = red_op<RED, T>(acc[k], u.e[k]);
+      }
     }
   }
-  T* dst = out + ((o * nsplit + s) * inner) + col * VEC;
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) dst[k] = acc[k];
+  for (int k = 0; k < VEC; ++k) sm[ty][tx * VEC + k] = acc[k];
+  __syncthreads();
+  if (ty == 0 && col < ncol) {
+    T* dst = out + ((o * nsplit + s) * inner) + col * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      T r = sm[0][tx * VEC + k];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) r = red_op<RED, T>(r, sm[j][tx * VEC + k]);
+      dst[k] = r;
+    }
+  }
 }
 
 template <int RED, typename T>
@@ -204,10 +219,10 @@ static int reduce_impl(T* out, const T* x, int64_t outer, int64_t red, int64_t i
   constexpr int VW = sizeof(T) == 4 ? 4 : 2;
   bool vec = (inner % VW == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   int64_t ncol = vec ? inner / VW : inner;
-  int64_t gx = ceil_div(ncol, 256);
+  int64_t gx = ceil_div(ncol, 32);
   int64_t nsplit = 1;
   if (gx * outer < target_ctas) {
-    nsplit = std::min<int64_t>(ceil_div(target_ctas, gx * outer), ceil_div(red, 16));
+    nsplit = std::min<int64_t>(ceil_div(target_ctas, gx * outer), ceil_div(red, 64));
     if (nsplit < 1) nsplit = 1;
   }
   if (outer * nsplit > 65535) {
