@@ -88,6 +88,8 @@ _SIGNATURES = {
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                         _c_i64, _c_vp, _c_int],
     "tnn_set_gemm_cta_group": [_c_int],
+    "tnn_set_gemm_ksplit": [_c_int],
+    "tnn_set_gemm_group_m": [_c_int],
     "tnn_relu_fwd": [_c_int, _c_vp, _c_vp, _c_i64],
     "tnn_relu_bwd": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_colsum": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
@@ -609,6 +611,12 @@ def set_gemm_cta_group(cg):
     load_library()
     if _lib.tnn_set_gemm_cta_group(int(cg)):
         _raise("tnn_set_gemm_cta_group")
+
+
+def set_gemm_ksplit(ks):
+    load_library()
+    if _lib.tnn_set_gemm_ksplit(int(ks)):
+        _raise("tnn_set_gemm_ksplit")
 
 
 def use_tensor_cores(M, N, K, dtype):

@@ -169,6 +169,13 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd,
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);
+/* Ordered split-K of the tcgen05 kernel: 0 = automatic (used when it fills the last wave of CTAs
+ * noticeably better, e.g. the 4096x4096x8192 dW products), 1 = off, 2 / 4 = forced.  The splits of
+ * a tile are added in a fixed order, so results are deterministic.  Also TNN_GEMM_KSPLIT. */
+int tnn_set_gemm_ksplit(int ks);
+/* Tile rasterisation of the tcgen05 kernel: consecutive tiles walk `gm` tile-rows before moving
+ * to the next tile column (1 = row-major order). */
+int tnn_set_gemm_group_m(int gm);
 
 /* ---- fused layer ops ----------------------------------------------------------------------- */
 /* ReLU = clip(x, 0.0) (layers.py:97-98); backward mask is x >= 0 (ops.py:336-343) */

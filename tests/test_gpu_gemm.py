@@ -81,6 +81,36 @@ def test_tf32x3_gemm_shapes(be, cg, shape):
         be.set_gemm_cta_group(0)
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("ks", [2, 4])
+def test_tf32x3_ordered_split_k(be, cg, ks):
+    """forced split-K: same result as the unsplit kernel to rounding, bit-identical run to run"""
+    rng = np.random.RandomState(11 * ks + cg)
+    M, N, K = 700, 520, 2304
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal((1, N)).astype(np.float32)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    da, db, dbias = be.from_numpy(a), be.from_numpy(b), be.from_numpy(bias)
+    ref = _ref(a, b, False, False, bias) + c0
+    old = be.TC_MIN_MNK
+    be.TC_MIN_MNK = 0
+    be.set_gemm_cta_group(cg)
+    be.set_gemm_ksplit(ks)
+    try:
+        outs = []
+        for _ in range(3):
+            dc = be.from_numpy(c0)
+            be.matmul(da, db, bias=dbias, out=dc, accumulate=True)
+            outs.append(dc.numpy())
+        assert op_cases.rel_err(outs[0], ref) <= TOL
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    finally:
+        be.set_gemm_ksplit(0)
+        be.set_gemm_cta_group(0)
+        be.TC_MIN_MNK = old
+
+
 def test_tf32x3_better_than_plain_tf32(be):
     """the split really buys fp32-level accuracy: error well below single-pass TF32 (~5e-4)"""
     rng = np.random.RandomState(1)

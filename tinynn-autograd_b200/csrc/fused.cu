@@ -230,23 +230,46 @@ ce_fold_loss_kernel(const T* nll, int64_t B, T m, T* loss) {
 
 // ---- cross entropy backward ---------------------------------------------------------------------
 // dz_kl = g * ( e_kl/S - (1/m) * y_kl * e_kl / (S * q_k) ),  e = exp(z - M)
-template <typename T, typename TY>
+template <typename T, typename TY, bool VEC>
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats, const T* q,
               T m, const T* gptr) {
-  // rows over blockIdx.y, columns over blockIdx.x * 256 + threadIdx.x: no per-element division
+  // rows over blockIdx.y, column slots over blockIdx.x * 256 + threadIdx.x: no per-element division.
+  // VEC: a slot is 4 consecutive columns moved with 128-bit (z, dz) / 128- or 256-bit (y) accesses.
+  constexpr int W = VEC ? 4 : 1;
   const T mx = stats[0], S = stats[1], g = gptr[0];
+  const int64_t nslot = C / W;
   for (int64_t r = blockIdx.y; r < B; r += gridDim.y) {
     const T qm = q[r] * m;
     const T* zr = z + r * C;
     const TY* yr = y + r * C;
     T* dr = dz + r * C;
-    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
-      T p = m_exp(zr[c] - mx) / S;
-      T yy = (T)yr[c];
-      T v = p;
-      if (yy != T(0)) v = p - (yy * p) / qm;
-      dr[c] = g * v;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < nslot; c += (int64_t)gridDim.x * 256) {
+      T zv[W], yv[W], out[W];
+      if constexpr (VEC) {
+        const float4 t = *reinterpret_cast<const float4*>(zr + c * 4);
+        zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
+        if constexpr (sizeof(TY) == 4) {
+          const float4 u = *reinterpret_cast<const float4*>(yr + c * 4);
+          yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+        } else {
+          const double2 u0 = *reinterpret_cast<const double2*>(yr + c * 4);
+          const double2 u1 = *reinterpret_cast<const double2*>(yr + c * 4 + 2);
+          yv[0] = (T)u0.x; yv[1] = (T)u0.y; yv[2] = (T)u1.x; yv[3] = (T)u1.y;
+        }
+      } else {
+        zv[0] = zr[c];
+        yv[0] = (T)yr[c];
+      }
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        T p = m_exp(zv[k] - mx) / S;
+        T v = p;
+        if (yv[k] != T(0)) v = p - (yv[k] * p) / qm;
+        out[k] = g * v;
+      }
+      if constexpr (VEC) *reinterpret_cast<float4*>(dr + c * 4) = make_float4(out[0], out[1], out[2], out[3]);
+      else dr[c] = out[0];
     }
   }
 }
@@ -432,10 +455,18 @@ template <typename T, typename TY>
 static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats,
                        const T* q, double m, const T* g) {
   cudaStream_t st = ctx().stream;
-  int gx = (int)std::min<int64_t>(ceil_div(C, 256), 64);
+  // the 128-bit path is float32 logits with 4-column-aligned rows
+  const bool vec = sizeof(T) == 4 && (C % 4 == 0) && al16(dz) && al16(z) && al16(y);
+  const int64_t nslot = vec ? C / 4 : C;
+  int gx = (int)std::min<int64_t>(ceil_div(nslot, 256), 64);
   int64_t gy = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)ctx().sm_count * 8 / gx));
   if (gy > 65535) gy = 65535;
-  ce_bwd_kernel<T, TY><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+  if (vec) {
+    if constexpr (sizeof(T) == 4)
+      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+  } else {
+    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+  }
   TNN_POST_LAUNCH();
   return 0;
 }

@@ -207,6 +207,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Tile rasterisation: consecutive tile ids walk group_m tile-rows before moving to the next tile
+// column.  group_m = 1 (row-major: the ~74 concurrent CTA pairs share ~5 A row-blocks and sweep
+// all B column-blocks) measured fastest on the wide-MLP shapes; squarer patches (4/8/16) lost
+// 1-15 %, so 1 is the default and the knob stays for other shapes.
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm,
+                                            int& tn) {
+  const int per_group = group_m * tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * group_m;
+  const int rows = min(group_m, tiles_m - first_m);
+  const int r = t - g * per_group;
+  tm = first_m + r % rows;
+  tn = r / rows;
+}
+
 // ---- the GEMM kernel ---------------------------------------------------------------------------
 template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -215,7 +230,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ D, int64_t ldd, int M, int N, int K,
-                   const float* __restrict__ bias, int flags) {
+                   const float* __restrict__ bias, int flags, int ksplit,
+                   unsigned int* __restrict__ tile_flags, int group_m) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -266,17 +282,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int num_kb = (K + BK - 1) / BK;
   const int group = blockIdx.x / CG;            // CTA (pair) index
   const int num_groups = gridDim.x / CG;
+  // Ordered split-K: a work unit is (tile, k-split).  Units [0, num_tiles) are the first k-range of
+  // every tile, [num_tiles, 2*num_tiles) the second, ...; split s > 0 adds onto what split s-1
+  // stored, in that fixed order (a per-tile arrival counter, never a floating-point atomic), so the
+  // result does not depend on timing.  Used when the tile count alone would leave a ragged last
+  // wave (the 4096x4096 dW products: 256 tiles on 74 CTA pairs).
+  const int num_units = num_tiles * ksplit;
+  const int kb_per_split = (num_kb + ksplit - 1) / ksplit;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = group; t < num_tiles; t += num_groups) {
-        const int tm = t / tiles_n, tn = t % tiles_n;
+      for (int u = group; u < num_units; u += num_groups) {
+        const int t = u % num_tiles, sp = u / num_tiles;
+        int tm, tn;
+        tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
         const int row_a = tm * C::TILE_M + (int)cta_rank * ROWS_A;
         const int row_b = tn * UMMA_N + (int)cta_rank * C::ROWS_B;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sa_lo = sa_hi + C::A_BYTES;
@@ -303,12 +329,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = group; t < num_tiles; t += num_groups) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+      for (int u = group; u < num_units; u += num_groups) {
+        const int sp = u / num_tiles;
+        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
-          const int kb1 = min(kb0 + CHUNK_KB, num_kb);
+          const int kb1 = min(kb0 + CHUNK_KB, kb_end);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -348,15 +376,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int half = (warp - 2) >> 2;                // accumulator columns [128*half, 128*half+128)
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool accumulate = flags & 1, relu = flags & 2;
-    for (int t = group; t < num_tiles; t += num_groups) {
-      const int tm = t / tiles_n, tn = t % tiles_n;
+    const bool relu = flags & 2;
+    for (int u = group; u < num_units; u += num_groups) {
+      const int t = u % num_tiles, sp = u / num_tiles;
+      const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+      const bool accumulate = (flags & 1) || sp > 0;
+      const float* bias_u = sp == 0 ? bias : nullptr;
+      int tm, tn;
+      tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
       const int row = tm * C::TILE_M + (int)cta_rank * ROWS_A + quad * 32 + lane;
       const int col0 = tn * UMMA_N + half * 128;
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
@@ -381,14 +414,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           acc_phase ^= 1u;
         }
       }
+      if (sp > 0) {
+        // wait until every epilogue warp of split sp-1 has stored this tile
+        if (lane == 0) {
+          const unsigned int need = (unsigned int)(sp * 8 * CG);
+          unsigned int seen;
+          long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tile_flags + t) : "memory");
+            if (clock64() - t0 > 8000000000LL) {
+              printf("tnn gemm_tc: split-K ordering wait timed out (tile %d split %d)\n", t, sp);
+              __trap();
+            }
+          } while (seen < need);
+        }
+        __syncwarp();
+        __threadfence();
+      }
       if (row < M && col0 < N) {
         float* drow = D + (int64_t)row * ldd;
         if (col0 + 128 <= N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 128; j += 4) {
             float4 v = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
-            if (bias) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);
+            if (bias_u) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_u + col0 + j);
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
             if (accumulate) {
@@ -406,13 +456,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           for (int j = 0; j < 128; ++j) {
             if (col0 + j < N) {
               float v = sum[j];
-              if (bias) v += bias[col0 + j];
+              if (bias_u) v += bias_u[col0 + j];
               if (accumulate) v += drow[col0 + j];
               if (relu) v = fmaxf(v, 0.f);
               drow[col0 + j] = v;
             }
           }
         }
+      }
+      if (sp + 1 < ksplit) {
+        // publish: this warp's part of the tile is in global memory
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(tile_flags + t, 1u);
       }
     }
   }
@@ -530,6 +586,11 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
 }
 
 constexpr int DEFAULT_CG = 2;  // CTA pairs: measured 0.98 ms vs 1.10 ms per 8192x4096x4096 product
+static unsigned int* g_tile_flags = nullptr;   // split-K arrival counters
+constexpr int MAX_FLAG_TILES = 1 << 16;
+static int g_group_m = 1;                      // tile rasterisation group; measured on 8192x4096x4096:
+                                               // 1 -> 0.95 ms, 4 -> 0.96-1.04, 8 -> 1.10, 16 -> 1.08
+static int g_force_ksplit = 0;                 // 0 = auto, 1 = off, 2/4 = forced (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3] = {false, false, false};
 
@@ -549,7 +610,24 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
     g_attr_set[CG] = true;
   }
   const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
-  int groups = (int)std::min<int64_t>(tiles, ctx().sm_count / CG);
+  const int max_groups = ctx().sm_count / CG;
+  // split-K factor.  Automatic mode only splits when the output has too few tiles to occupy half
+  // the chip (tall-skinny products with a long K); measured on the wide MLP's 4096x4096x8192 dW
+  // product, splitting to fix its ragged last wave (256 tiles on 74 pairs) LOST time (1.20 ms vs
+  // 1.03 ms): the second split's read-modify-write epilogue costs more than the idle tail.
+  // The ReLU epilogue needs the complete sum, so it never splits.
+  int ksplit = 1;
+  if (!(flags & 2) && tiles <= MAX_FLAG_TILES && g_force_ksplit != 1) {
+    const int64_t num_kb = ceil_div(K, BK);
+    for (int s = 2; s <= 4; s *= 2)
+      if (tiles * s <= max_groups && num_kb / s >= 16) ksplit = s;
+    if (g_force_ksplit > 1 && num_kb / g_force_ksplit >= 1) ksplit = g_force_ksplit;
+  }
+  if (ksplit > 1) {
+    if (!g_tile_flags) TNN_CUDA(cudaMalloc(&g_tile_flags, MAX_FLAG_TILES * sizeof(unsigned int)));
+    TNN_CUDA(cudaMemsetAsync(g_tile_flags, 0, (size_t)tiles * sizeof(unsigned int), ctx().stream));
+  }
+  int groups = (int)std::min<int64_t>(tiles * ksplit, max_groups);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
   cfg.blockDim = dim3(NUM_THREADS);
@@ -563,7 +641,7 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(1);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, ksplit, g_tile_flags, g_group_m));
   ctx().launches++;
   prof_end(1);
   return 0;
@@ -594,6 +672,18 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C, float* hi, float* lo, i
   return 0;
 }
 
+int tnn_set_gemm_group_m(int gm) {
+  if (gm < 1 || gm > 64) TNN_FAIL("tnn_set_gemm_group_m: 1..64");
+  tc::g_group_m = gm;
+  return 0;
+}
+
+int tnn_set_gemm_ksplit(int ks) {
+  if (ks != 0 && ks != 1 && ks != 2 && ks != 4) TNN_FAIL("tnn_set_gemm_ksplit: 0 (auto), 1 (off), 2 or 4");
+  tc::g_force_ksplit = ks;
+  return 0;
+}
+
 int tnn_set_gemm_cta_group(int cg) {
   if (cg != 0 && cg != 1 && cg != 2) TNN_FAIL("tnn_set_gemm_cta_group: 0 (default), 1 or 2");
   tc::g_force_cg = cg;
@@ -612,6 +702,8 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
   if (!env_read) {
     const char* e = getenv("TNN_GEMM_CG");
     if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
+    const char* ks = getenv("TNN_GEMM_KSPLIT");
+    if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
     env_read = true;
   }
   int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
