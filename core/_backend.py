@@ -86,7 +86,7 @@ _SIGNATURES = {
                       _c_i64, _c_i64, _c_vp, _c_int],
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                        _c_i64, _c_vp, _c_int],
+                        _c_i64, _c_vp, _c_int, _c_int],
     "tnn_set_gemm_cta_group": [_c_int],
     "tnn_set_gemm_ksplit": [_c_int],
     "tnn_set_gemm_group_m": [_c_int],
@@ -564,6 +564,7 @@ def scatter_flat(g, idx_dev, shape):
 # --------------------------------------------------------------------------------------------
 TC_MIN_MNK = int(os.environ.get("TNN_TC_MIN_MNK", str(1 << 26)))
 TC_ENABLED = os.environ.get("TNN_TC", "1") != "0"
+TC_MN_MAJOR = os.environ.get("TNN_TC_MN_MAJOR", "1") != "0"   # 0: transposed tf32 planes instead
 _split_epoch = 0
 
 
@@ -654,10 +655,17 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         return out
     flags = (1 if accumulate else 0) | (2 if relu else 0)
     if K > 0 and use_tensor_cores(M, N, K, dt):
-        a_hi, a_lo, lda = split_planes(a, transposed=ta, also_other=reuse_a)
-        b_hi, b_lo, ldb = split_planes(b, transposed=not tb, also_other=reuse_b)
+        if TC_MN_MAJOR:
+            # un-transposed planes only: a transposed operand is fed MN-major to the tensor core
+            a_hi, a_lo, lda = split_planes(a, transposed=False)
+            b_hi, b_lo, ldb = split_planes(b, transposed=False)
+            layout = (1 if ta else 0) | (0 if tb else 2)
+        else:
+            a_hi, a_lo, lda = split_planes(a, transposed=ta, also_other=reuse_a)
+            b_hi, b_lo, ldb = split_planes(b, transposed=not tb, also_other=reuse_b)
+            layout = 0
         if _lib.tnn_gemm_tf32x3(out.ptr, N, a_hi.ptr, a_lo.ptr, lda, b_hi.ptr, b_lo.ptr, ldb, M, N,
-                                K, bias.ptr if bias is not None else None, flags):
+                                K, bias.ptr if bias is not None else None, flags, layout):
             _raise("tnn_gemm_tf32x3")
         return out
     a_rs, a_cs = (1, a.shape[1]) if ta else (a.shape[1], 1)

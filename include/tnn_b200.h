@@ -159,13 +159,15 @@ int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs, 
  * transposed    hiT/loT: [C, ldt]  (ldt >= R, multiple of 4)   -- may be NULL */
 int tnn_split_tf32(const float* x, int64_t R, int64_t C,
                    float* hi, float* lo, int64_t ldp, float* hiT, float* loT, int64_t ldt);
-/* tcgen05 3xTF32: D[M,N] (ldd) = A[M,K] * B[N,K]^T with both operands K-major hi/lo planes.
+/* tcgen05 3xTF32: D[M,N] (ldd) = A[M,K] * B[K,N] from tf32 hi/lo planes.
+ * layout bit0 = 0: A planes are K-major, stored [M, lda] (k contiguous);  1: MN-major, stored [K, lda]
+ * layout bit1 = 0: B planes are K-major, stored [N, ldb] (k contiguous);  2: MN-major, stored [K, ldb]
+ * so X@W is layout 2, G@W.T is layout 0 and X.T@G is layout 3, all on un-transposed planes.
  * flags bit0 = accumulate into D, bit1 = relu on the output; bias[N] may be NULL. */
 int tnn_gemm_tf32x3(float* D, int64_t ldd,
                     const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb,
-                    int64_t M, int64_t N, int64_t K, const float* bias, int flags);
-
+                    int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout);
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);

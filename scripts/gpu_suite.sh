@@ -24,11 +24,13 @@ for s in $STAGES; do
     bench_n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/bench_n4.log 2>&1 ;;
     bench_n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/bench_n8.log 2>&1 ;;
     bench1) timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1 ;;
+    memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_autograd_cases.py tests/test_gpu_gemm.py -m gpu -q -x -p no:cacheprovider > gpurun_out/memcheck.log 2>&1 ;;
+    gemmbench) timeout 600 python scripts/gemm_bench.py --cg 1,2 --ksplit 1 --group-m 1 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt
 done
-for f in gpurun_out/smoke.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
+for f in gpurun_out/smoke.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/memcheck.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
   [ -f $f ] && { echo "== $f"; tail -n 6 $f; }
 done
 cat gpurun_out/stages.txt

@@ -42,14 +42,19 @@ def test_split_planes_reconstruct(be):
         assert np.array_equal(HT, H.T) and np.array_equal(LT, L.T)
 
 
+@pytest.mark.parametrize("mn_major", [True, False])
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("shape", [
     (128, 256, 32), (128, 256, 64), (256, 256, 128), (256, 512, 96), (384, 768, 200),
     (100, 300, 52), (129, 257, 36), (1000, 520, 260), (2048, 1024, 512),
 ])
-def test_tf32x3_gemm_shapes(be, cg, shape):
+def test_tf32x3_gemm_shapes(be, cg, shape, mn_major):
+    """NN / NT / TN products; mn_major=True feeds transposed operands MN-major from the plain tf32
+    planes (default), False goes through transposed planes (both operands K-major)"""
     M, N, K = shape
     be.set_gemm_cta_group(cg)
+    old_mn = be.TC_MN_MAJOR
+    be.TC_MN_MAJOR = mn_major
     try:
         rng = np.random.RandomState(M * 7 + N * 3 + K)
         a = rng.standard_normal((M, K)).astype(np.float32)
@@ -78,6 +83,7 @@ def test_tf32x3_gemm_shapes(be, cg, shape):
         finally:
             be.TC_MIN_MNK = old
     finally:
+        be.TC_MN_MAJOR = old_mn
         be.set_gemm_cta_group(0)
 
 

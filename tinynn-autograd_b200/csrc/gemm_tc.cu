@@ -193,18 +193,30 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+// Operand tiles in shared memory (one plane of one 32-wide K block, rows = 128 M/N rows):
+//   K-major  : one TMA box {32 k, rows}: row r at r*128 B, k contiguous, 128-byte swizzle.
+//              Descriptor: 8-row groups 1024 B apart (SBO); a K=8 step advances 32 B in the row.
+//   MN-major : rows/32 TMA boxes {32 mn, 32 k} of 4096 B each: inside a box k-row j at j*128 B with
+//              32 consecutive M/N elements.  32-bit MN-major operands only exist in the
+//              "128-byte swizzle with 32-byte atoms" layout (TMA SWIZZLE_128B_ATOM_32B, UMMA layout
+//              type SWIZZLE_128B_BASE32B): the swizzle pattern spans 4 k-rows (512 B).  Descriptor:
+//              4-k groups 512 B apart (SBO), 32-element M/N chunks 4096 B apart (LBO); a K=8 step
+//              advances 1024 B.
+template <bool MN>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address
-  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
-  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                  // start address
+  d |= (uint64_t)(MN ? (4096 >> 4) : 1) << 16;               // leading byte offset
+  d |= (uint64_t)((MN ? 512 : 1024) >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                                    // descriptor version (Blackwell)
+  d |= (uint64_t)(MN ? 1 : 2) << 61;                         // SWIZZLE_128B_BASE32B : SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N, M
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+constexpr int MN_BOX_BYTES = 32 * PLANE_ROW_BYTES;           // one {32 mn, 32 k} box
+// instruction descriptor: D=F32, A=B=TF32, operand majors, N, M
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Tile rasterisation: consecutive tile ids walk group_m tile-rows before moving to the next tile
@@ -223,7 +235,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 }
 
 // ---- the GEMM kernel ---------------------------------------------------------------------------
-template <int CG>
+template <int CG, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_a_lo,
@@ -310,10 +322,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t sb_lo = sb_hi + C::B_BYTES;
           if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)C::STAGE_BYTES * CG);
           const int k0 = kb * BK;
-          tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
-          tma_load_2d<CG>(sa_lo, &map_a_lo, full_bar(stage), k0, row_a);
-          tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
-          tma_load_2d<CG>(sb_lo, &map_b_lo, full_bar(stage), k0, row_b);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < ROWS_A / 32; ++j) {
+              tma_load_2d<CG>(sa_hi + j * MN_BOX_BYTES, &map_a_hi, full_bar(stage), row_a + 32 * j, k0);
+              tma_load_2d<CG>(sa_lo + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 32 * j, k0);
+            }
+          } else {
+            tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
+            tma_load_2d<CG>(sa_lo, &map_a_lo, full_bar(stage), k0, row_a);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int j = 0; j < C::ROWS_B / 32; ++j) {
+              tma_load_2d<CG>(sb_hi + j * MN_BOX_BYTES, &map_b_hi, full_bar(stage), row_b + 32 * j, k0);
+              tma_load_2d<CG>(sb_lo + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 32 * j, k0);
+            }
+          } else {
+            tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
+            tma_load_2d<CG>(sb_lo, &map_b_lo, full_bar(stage), k0, row_b);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -324,7 +352,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(C::TILE_M, UMMA_N);
+      constexpr uint32_t idesc = make_idesc(C::TILE_M, UMMA_N, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -346,11 +374,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint32_t sb_lo = sb_hi + C::B_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t koff = (uint32_t)(k * UMMA_K * 4);  // bytes inside the 128-byte row
-              const uint64_t da_hi = make_smem_desc(sa_hi + koff);
-              const uint64_t da_lo = make_smem_desc(sa_lo + koff);
-              const uint64_t db_hi = make_smem_desc(sb_hi + koff);
-              const uint64_t db_lo = make_smem_desc(sb_lo + koff);
+              // a K=8 step: 32 B along the row (K-major) or one 8-row group of 1024 B (MN-major)
+              const uint32_t koff_a = (uint32_t)(k * (A_MN ? 1024 : UMMA_K * 4));
+              const uint32_t koff_b = (uint32_t)(k * (B_MN ? 1024 : UMMA_K * 4));
+              const uint64_t da_hi = make_smem_desc<A_MN>(sa_hi + koff_a);
+              const uint64_t da_lo = make_smem_desc<A_MN>(sa_lo + koff_a);
+              const uint64_t db_hi = make_smem_desc<B_MN>(sb_hi + koff_b);
+              const uint64_t db_lo = make_smem_desc<B_MN>(sb_lo + koff_b);
               // small terms first; the first MMA of a chunk overwrites the accumulator
               umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
               umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
@@ -571,15 +601,19 @@ static int get_encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, K] with row pitch ld (elements); box = [BK, box_rows], 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+// K-major plane [rows, K] (pitch ld): box {BK k, box_rows}.  MN-major plane [K, rows] (pitch ld):
+// box {32 mn, BK k}.
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                    bool mn_major) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) TNN_FAIL("tf32x3 GEMM: operand plane must be 16-byte aligned");
   if (ld % 4 != 0) TNN_FAIL("tf32x3 GEMM: operand pitch must be a multiple of 4 elements");
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 32 : BK), (cuuint32_t)(mn_major ? BK : box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) TNN_FAIL("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
@@ -592,22 +626,22 @@ static int g_group_m = 1;                      // tile rasterisation group; meas
                                                // 1 -> 0.95 ms, 4 -> 0.96-1.04, 8 -> 1.10, 16 -> 1.08
 static int g_force_ksplit = 0;                 // 0 = auto, 1 = off, 2/4 = forced (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
-static bool g_attr_set[3] = {false, false, false};
+static bool g_attr_set[3][2][2] = {};
 
-template <int CG>
+template <int CG, bool A_MN, bool B_MN>
 static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                        const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
                        int64_t K, const float* bias, int flags) {
   using C = Cfg<CG>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (make_map(&ma_hi, a_hi, M, K, lda, ROWS_A)) return 1;
-  if (make_map(&ma_lo, a_lo, M, K, lda, ROWS_A)) return 1;
-  if (make_map(&mb_hi, b_hi, N, K, ldb, C::ROWS_B)) return 1;
-  if (make_map(&mb_lo, b_lo, N, K, ldb, C::ROWS_B)) return 1;
-  auto kern = gemm_tf32x3_kernel<CG>;
-  if (!g_attr_set[CG]) {
+  if (make_map(&ma_hi, a_hi, M, K, lda, ROWS_A, A_MN)) return 1;
+  if (make_map(&ma_lo, a_lo, M, K, lda, ROWS_A, A_MN)) return 1;
+  if (make_map(&mb_hi, b_hi, N, K, ldb, C::ROWS_B, B_MN)) return 1;
+  if (make_map(&mb_lo, b_lo, N, K, ldb, C::ROWS_B, B_MN)) return 1;
+  auto kern = gemm_tf32x3_kernel<CG, A_MN, B_MN>;
+  if (!g_attr_set[CG][A_MN][B_MN]) {
     TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    g_attr_set[CG] = true;
+    g_attr_set[CG][A_MN][B_MN] = true;
   }
   const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
   const int max_groups = ctx().sm_count / CG;
@@ -652,6 +686,18 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
 
 using namespace tnn;
 
+template <int CG>
+static int launch_by_layout(int layout, float* D, int64_t ldd, const float* a_hi, const float* a_lo,
+                            int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, int64_t M,
+                            int64_t N, int64_t K, const float* bias, int flags) {
+  switch (layout & 3) {
+    case 0: return tnn::tc::launch_gemm<CG, false, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    case 1: return tnn::tc::launch_gemm<CG, true, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    case 2: return tnn::tc::launch_gemm<CG, false, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    default: return tnn::tc::launch_gemm<CG, true, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+  }
+}
+
 extern "C" {
 
 int tnn_split_tf32(const float* x, int64_t R, int64_t C, float* hi, float* lo, int64_t ldp,
@@ -692,7 +738,7 @@ int tnn_set_gemm_cta_group(int cg) {
 
 int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
-                    int64_t K, const float* bias, int flags) {
+                    int64_t K, const float* bias, int flags, int layout) {
   TNN_REQUIRE_INIT();
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) TNN_FAIL("tnn_gemm_tf32x3: K must be positive");
@@ -708,8 +754,8 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
   }
   int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
   if (cg == 2)
-    return tc::launch_gemm<2>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
-  return tc::launch_gemm<1>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    return launch_by_layout<2>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+  return launch_by_layout<1>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
 }
 
 }  // extern "C"
