@@ -171,9 +171,10 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd,
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);
-/* Ordered split-K of the tcgen05 kernel: 0 = automatic (used when it fills the last wave of CTAs
- * noticeably better, e.g. the 4096x4096x8192 dW products), 1 = off, 2 / 4 = forced.  The splits of
- * a tile are added in a fixed order, so results are deterministic.  Also TNN_GEMM_KSPLIT. */
+/* Ordered split-K of the tcgen05 kernel: 0 = automatic (only the tiles of a ragged last wave are
+ * cut along K, e.g. the 4096x4096x8192 dW products: 256 tiles on 74 CTA pairs), 1 = off, 2 / 4 =
+ * every tile.  The K ranges of a tile are added in a fixed order, so results are deterministic.
+ * Also TNN_GEMM_KSPLIT. */
 int tnn_set_gemm_ksplit(int ks);
 /* Tile rasterisation of the tcgen05 kernel: consecutive tiles walk `gm` tile-rows before moving
  * to the next tile column (1 = row-major order). */

@@ -242,7 +242,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ D, int64_t ldd, int M, int N, int K,
-                   const float* __restrict__ bias, int flags, int ksplit,
+                   const float* __restrict__ bias, int flags, int t_full, int tail_split,
                    unsigned int* __restrict__ tile_flags, int group_m) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
@@ -294,13 +294,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int num_kb = (K + BK - 1) / BK;
   const int group = blockIdx.x / CG;            // CTA (pair) index
   const int num_groups = gridDim.x / CG;
-  // Ordered split-K: a work unit is (tile, k-split).  Units [0, num_tiles) are the first k-range of
-  // every tile, [num_tiles, 2*num_tiles) the second, ...; split s > 0 adds onto what split s-1
-  // stored, in that fixed order (a per-tile arrival counter, never a floating-point atomic), so the
-  // result does not depend on timing.  Used when the tile count alone would leave a ragged last
-  // wave (the 4096x4096 dW products: 256 tiles on 74 CTA pairs).
-  const int num_units = num_tiles * ksplit;
-  const int kb_per_split = (num_kb + ksplit - 1) / ksplit;
+  // Work units.  Tiles [0, t_full) are whole-K units.  The remaining "tail" tiles -- the ones that
+  // would form a ragged last wave (4096x4096 dW product: 256 tiles on 74 CTA pairs = 3 full waves
+  // + 34 tiles) -- are cut into tail_split K ranges each, so the last wave is short AND full:
+  // unit t_full + j covers tile t_full + j % rem, K range j / rem.  Range s > 0 adds onto what
+  // range s-1 stored, in that fixed order (a per-tile arrival counter gates the read-modify-write;
+  // never a floating-point atomic), so the result does not depend on timing.
+  const int tail_rem = num_tiles - t_full;
+  const int num_units = t_full + tail_rem * tail_split;
+  const int kb_per_split = (num_kb + tail_split - 1) / tail_split;
+  auto decode = [&](int u, int& t, int& sp, int& kb_begin, int& kb_end) {
+    if (u < t_full) {
+      t = u; sp = 0; kb_begin = 0; kb_end = num_kb;
+    } else {
+      const int j = u - t_full;
+      t = t_full + j % tail_rem;
+      sp = j / tail_rem;
+      kb_begin = sp * kb_per_split;
+      kb_end = min(num_kb, kb_begin + kb_per_split);
+    }
+  };
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -308,12 +321,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int stage = 0;
       uint32_t phase = 0;
       for (int u = group; u < num_units; u += num_groups) {
-        const int t = u % num_tiles, sp = u / num_tiles;
+        int t, sp, kb_begin, kb_end;
+        decode(u, t, sp, kb_begin, kb_end);
         int tm, tn;
         tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
         const int row_a = tm * C::TILE_M + (int)cta_rank * ROWS_A;
         const int row_b = tn * UMMA_N + (int)cta_rank * C::ROWS_B;
-        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
@@ -358,8 +371,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int u = group; u < num_units; u += num_groups) {
-        const int sp = u / num_tiles;
-        const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+        int t, sp, kb_begin, kb_end;
+        decode(u, t, sp, kb_begin, kb_end);
         for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
           tc_fence_after();
@@ -408,8 +421,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     uint32_t acc_phase = 0;
     const bool relu = flags & 2;
     for (int u = group; u < num_units; u += num_groups) {
-      const int t = u % num_tiles, sp = u / num_tiles;
-      const int kb_begin = sp * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+      int t, sp, kb_begin, kb_end;
+      decode(u, t, sp, kb_begin, kb_end);
       const bool accumulate = (flags & 1) || sp > 0;
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
@@ -494,7 +507,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
         }
       }
-      if (sp + 1 < ksplit) {
+      if (u >= t_full && sp + 1 < tail_split) {
         // publish: this warp's part of the tile is in global memory
         __threadfence();
         __syncwarp();
@@ -624,7 +637,7 @@ static unsigned int* g_tile_flags = nullptr;   // split-K arrival counters
 constexpr int MAX_FLAG_TILES = 1 << 16;
 static int g_group_m = 1;                      // tile rasterisation group; measured on 8192x4096x4096:
                                                // 1 -> 0.95 ms, 4 -> 0.96-1.04, 8 -> 1.10, 16 -> 1.08
-static int g_force_ksplit = 0;                 // 0 = auto, 1 = off, 2/4 = forced (TNN_GEMM_KSPLIT)
+static int g_force_ksplit = 0;                 // 0 = auto (tail split), 1 = off, 2/4 = every tile (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3][2][2] = {};
 
@@ -645,23 +658,38 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   }
   const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
   const int max_groups = ctx().sm_count / CG;
-  // split-K factor.  Automatic mode only splits when the output has too few tiles to occupy half
-  // the chip (tall-skinny products with a long K); measured on the wide MLP's 4096x4096x8192 dW
-  // product, splitting to fix its ragged last wave (256 tiles on 74 pairs) LOST time (1.20 ms vs
-  // 1.03 ms): the second split's read-modify-write epilogue costs more than the idle tail.
-  // The ReLU epilogue needs the complete sum, so it never splits.
-  int ksplit = 1;
+  // Tail split (see the kernel): when the tile count leaves a ragged last wave, the tiles of that
+  // wave are cut along K so it runs short and full.  Measured on the 4096x4096x8192 dW product
+  // (256 tiles, 74 CTA pairs): see profiles/.  Splitting EVERY tile instead lost time (1.20 ms vs
+  // 1.03 ms, the read-modify-write epilogue of the second range costs more than the idle tail), so
+  // a forced whole-matrix split is only taken when asked for.  The ReLU epilogue needs the complete
+  // sum, so it never splits.
+  int t_full = (int)tiles, tail_split = 1;
   if (!(flags & 2) && tiles <= MAX_FLAG_TILES && g_force_ksplit != 1) {
     const int64_t num_kb = ceil_div(K, BK);
-    for (int s = 2; s <= 4; s *= 2)
-      if (tiles * s <= max_groups && num_kb / s >= 16) ksplit = s;
-    if (g_force_ksplit > 1 && num_kb / g_force_ksplit >= 1) ksplit = g_force_ksplit;
+    if (g_force_ksplit > 1) {
+      if (num_kb / g_force_ksplit >= 1) {
+        t_full = 0;
+        tail_split = g_force_ksplit;
+      }
+    } else {
+      const int64_t rem = tiles % max_groups;
+      if (rem > 0) {
+        int s = 1;
+        while (s < 4 && rem * (s * 2) <= max_groups && num_kb / (s * 2) >= 16) s *= 2;
+        if (s > 1) {
+          t_full = (int)(tiles - rem);
+          tail_split = s;
+        }
+      }
+    }
   }
-  if (ksplit > 1) {
+  if (tail_split > 1) {
     if (!g_tile_flags) TNN_CUDA(cudaMalloc(&g_tile_flags, MAX_FLAG_TILES * sizeof(unsigned int)));
     TNN_CUDA(cudaMemsetAsync(g_tile_flags, 0, (size_t)tiles * sizeof(unsigned int), ctx().stream));
   }
-  int groups = (int)std::min<int64_t>(tiles * ksplit, max_groups);
+  const int64_t units = t_full + (tiles - t_full) * tail_split;
+  int groups = (int)std::min<int64_t>(units, max_groups);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
   cfg.blockDim = dim3(NUM_THREADS);
@@ -675,7 +703,7 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(1);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, ksplit, g_tile_flags, g_group_m));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m));
   ctx().launches++;
   prof_end(1);
   return 0;
