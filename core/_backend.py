@@ -83,10 +83,10 @@ _SIGNATURES = {
     "tnn_gather_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_scatter_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_simt": [_c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64,
-                      _c_i64, _c_i64, _c_vp, _c_int],
+                      _c_i64, _c_i64, _c_vp, _c_int, _c_vp],
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                        _c_i64, _c_vp, _c_int, _c_int],
+                        _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_set_gemm_cta_group": [_c_int],
     "tnn_set_gemm_ksplit": [_c_int],
     "tnn_set_gemm_group_m": [_c_int],
@@ -626,13 +626,17 @@ def use_tensor_cores(M, N, K, dtype):
 
 
 def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu=False,
-           reuse_a=False, reuse_b=False):
+           reuse_a=False, reuse_b=False, act=False):
     """op(a) @ op(b) (+ bias) for 2-D arrays; op = transpose when ta/tb (ops.py:150-160).
 
     float32 products above TC_MIN_MNK run on the tcgen05 3xTF32 kernel; float64 and small or
     odd-shaped products run on the SIMT kernel.  reuse_a/reuse_b hint that the other orientation
     of that operand will be needed later in the step (forward -> backward), so both sets of tf32
-    planes are produced by one pass."""
+    planes are produced by one pass.
+
+    act=True returns (out, relu(out)): the GEMM epilogue writes the ReLU of its result as a second
+    array -- and, on the tensor-core path, that array's tf32 planes, which are attached to it so the
+    next product consumes it without a separate ReLU or split pass."""
     if a.ndim != 2 or b.ndim != 2:
         raise ValueError("matmul: only 2-D operands are supported (got %s @ %s)" % (a.shape, b.shape))
     dt = _common_dtype(a, b)
@@ -651,8 +655,9 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         raise ValueError("matmul: bad output array")
     if bias is not None and bias.dtype != dt:
         bias = astype(bias, dt)
+    act_out = empty((M, N), dt) if act else None
     if M == 0 or N == 0:
-        return out
+        return (out, act_out) if act else out
     flags = (1 if accumulate else 0) | (2 if relu else 0)
     if K > 0 and use_tensor_cores(M, N, K, dt):
         if TC_MN_MAJOR:
@@ -664,19 +669,29 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
             a_hi, a_lo, lda = split_planes(a, transposed=ta, also_other=reuse_a)
             b_hi, b_lo, ldb = split_planes(b, transposed=not tb, also_other=reuse_b)
             layout = 0
+        act_hi = act_lo = None
+        ld_act = _round4(N)
+        if act:
+            act_hi, act_lo = empty((M, ld_act), F32), empty((M, ld_act), F32)
         if _lib.tnn_gemm_tf32x3(out.ptr, N, a_hi.ptr, a_lo.ptr, lda, b_hi.ptr, b_lo.ptr, ldb, M, N,
-                                K, bias.ptr if bias is not None else None, flags, layout):
+                                K, bias.ptr if bias is not None else None, flags, layout,
+                                act_out.ptr if act else None, act_hi.ptr if act else None,
+                                act_lo.ptr if act else None, ld_act):
             _raise("tnn_gemm_tf32x3")
+        if act:
+            act_out.split = {"epoch": _split_epoch, "p": (act_hi, act_lo, ld_act)}
+            return out, act_out
         return out
     a_rs, a_cs = (1, a.shape[1]) if ta else (a.shape[1], 1)
     b_rs, b_cs = (1, b.shape[1]) if tb else (b.shape[1], 1)
     if _lib.tnn_gemm_simt(_DT_CODE[dt], out.ptr, N, a.ptr, a_rs, a_cs, b.ptr, b_rs, b_cs, M, N, K,
-                          bias.ptr if bias is not None else None, flags & 1):
+                          bias.ptr if bias is not None else None, flags & 1,
+                          act_out.ptr if act else None):
         _raise("tnn_gemm_simt")
     if relu:
         if _lib.tnn_relu_fwd(_DT_CODE[dt], out.ptr, out.ptr, out.size):
             _raise("tnn_relu_fwd")
-    return out
+    return (out, act_out) if act else out
 
 
 # --------------------------------------------------------------------------------------------

@@ -42,6 +42,16 @@ class Dense(Layer):
         self.inputs = inputs
         return ops.dense_(inputs, self.params["w"], self.params["b"])
 
+    def forward_fused_relu(self, inputs, relu_layer):
+        """this layer followed by `relu_layer` in one GEMM launch (core.nn.Net calls this when a
+        Dense is directly followed by a ReLU); both layers record their inputs as usual"""
+        if not self.is_init:
+            self._init_parameters(inputs.shape[1])
+        self.inputs = inputs
+        z, a = ops.dense_relu_(inputs, self.params["w"], self.params["b"])
+        relu_layer.inputs = z
+        return a
+
     def _init_parameters(self, input_size):
         # layers.py:51-57; draw order (w then b) fixes the numpy RNG stream
         self.shapes["w"][0] = input_size

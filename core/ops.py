@@ -440,6 +440,12 @@ def dense_(ts_x, ts_w, ts_b):
     if b.shape != (1, w.shape[1]) or x.dtype != w.dtype or b.dtype != w.dtype:
         return ts_x @ ts_w + ts_b
     values = be.matmul(x, w, bias=b, reuse_a=ts_w.requires_grad, reuse_b=ts_x.requires_grad)
+    return _dense_node(ts_x, ts_w, ts_b, values)
+
+
+def _dense_node(ts_x, ts_w, ts_b, values):
+    """graph node of x@w+b: dX = g@w.T, dW = x.T@g, db = column sum of g"""
+    x, w = ts_x._data, ts_w._data
 
     def grad_fn_x(grad, out=None, accumulate=False):
         return be.matmul(grad, w, tb=True, out=out, accumulate=accumulate,
@@ -462,6 +468,24 @@ def dense_(ts_x, ts_w, ts_b):
             dependency.append(dict(tensor=t, grad_fn=fn))
     requires_grad = ts_x.requires_grad or ts_w.requires_grad or ts_b.requires_grad
     return ts_x.__class__(values, requires_grad, dependency)
+
+
+def dense_relu_(ts_x, ts_w, ts_b):
+    """Dense followed by ReLU (layers.py:49 then layers.py:97-98) computed by ONE GEMM launch whose
+    epilogue writes both the pre-activation z = x@w+b and a = clip(z, 0).  The graph is the same two
+    nodes the unfused layers build (z depends on x, w, b; a depends on z with the x >= 0 mask), so
+    gradients, non-leaf .grad and Activation.inputs are unchanged.  Returns (z, a)."""
+    x, w, b = ts_x._data, ts_w._data, ts_b._data
+    if b.shape != (1, w.shape[1]) or x.dtype != w.dtype or b.dtype != w.dtype:
+        z = ts_x @ ts_w + ts_b
+        return z, relu_(z)
+    zv, av = be.matmul(x, w, bias=b, reuse_a=ts_w.requires_grad, reuse_b=ts_x.requires_grad, act=True)
+    ts_z = _dense_node(ts_x, ts_w, ts_b, zv)
+
+    def relu_grad(grad):
+        return be.relu_bwd(grad, zv)
+
+    return ts_z, build_unary_ops_tensor(ts_z, relu_grad, av)
 
 
 def softmax_ce_(ts_logits, ts_labels):

@@ -150,10 +150,11 @@ int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev
 
 /* ---- GEMM (ops.py:150-163 dot_: A@B, grad@B.T, A.T@grad) ----------------------------------- */
 /* SIMT path, any shape, f32/f64.  C[M,N] (ldc) = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C).
- * A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]; flags bit0 = accumulate into C. */
+ * A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]; flags bit0 = accumulate into C.
+ * act_out (may be NULL, pitch ldc) additionally receives ReLU(C): Dense + ReLU in one launch. */
 int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs, int64_t a_cs,
                   const void* B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                  const void* bias, int flags);
+                  const void* bias, int flags, void* act_out);
 /* fp32 -> (hi, lo) tf32 planes for the 3xTF32 tensor-core GEMM.  x is [R, C] row-major (ld = C).
  * plain planes  hi/lo  : [R, ldp]  (ldp >= C, multiple of 4)   -- may be NULL
  * transposed    hiT/loT: [C, ldt]  (ldt >= R, multiple of 4)   -- may be NULL */
@@ -163,11 +164,16 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C,
  * layout bit0 = 0: A planes are K-major, stored [M, lda] (k contiguous);  1: MN-major, stored [K, lda]
  * layout bit1 = 0: B planes are K-major, stored [N, ldb] (k contiguous);  2: MN-major, stored [K, ldb]
  * so X@W is layout 2, G@W.T is layout 0 and X.T@G is layout 3, all on un-transposed planes.
- * flags bit0 = accumulate into D, bit1 = relu on the output; bias[N] may be NULL. */
+ * flags bit0 = accumulate into D, bit1 = relu on the output; bias[N] may be NULL.
+ * Fused activation outputs (Dense -> ReLU -> next Dense without extra passes, layers.py:49,97-98):
+ * act_out (may be NULL, pitch ldd) receives ReLU(D) while D keeps the pre-activation the ReLU
+ * backward mask needs; act_hi/act_lo (may be NULL, pitch ld_act) receive the tf32 planes of
+ * ReLU(D), i.e. the A operand of the next layer's product. */
 int tnn_gemm_tf32x3(float* D, int64_t ldd,
                     const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb,
-                    int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout);
+                    int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout,
+                    float* act_out, float* act_hi, float* act_lo, int64_t ld_act);
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);

@@ -26,6 +26,7 @@ for s in $STAGES; do
     bench1) timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1 ;;
     memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_autograd_cases.py tests/test_gpu_gemm.py -m gpu -q -x -p no:cacheprovider > gpurun_out/memcheck.log 2>&1 ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0,1 --group-m 1 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
+    ab_fuse) for i in 1 2 3; do TNN_FUSE_RELU=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse1.log 2>&1; TNN_FUSE_RELU=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse0.log 2>&1; done ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt

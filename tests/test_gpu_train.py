@@ -218,6 +218,47 @@ def test_tensor_core_mlp_step_teacher_forced(cg):
         be.set_gemm_cta_group(0)
 
 
+@pytest.mark.parametrize("size", [(16, 20, 12, 8), (512, 256, 384, 128)])
+def test_dense_relu_fusion_is_transparent(size):
+    """Net.forward runs Dense+ReLU as one GEMM launch (ReLU and the next layer's tf32 planes come
+    out of the epilogue); values, recorded layer inputs and every gradient are bit-identical to
+    calling the layers one by one (small = SIMT kernel, large = tcgen05 kernel)"""
+    import core._backend as be
+    from core.layers import Dense, ReLU
+    from core.losses import SoftmaxCrossEntropyLoss
+    from core.nn import Net
+    from core.tensor import Tensor
+    B, D, H, C = size
+    rng = np.random.RandomState(7)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    labels = np.eye(C, dtype=np.float32)[rng.randint(0, C, B)]
+    old = be.TC_MIN_MNK
+    be.TC_MIN_MNK = 1 << 22
+    try:
+        outs = []
+        for fused in (True, False):
+            np.random.seed(11)
+            layers = [Dense(H), ReLU(), Dense(H), ReLU(), Dense(C)]
+            net = Net(layers)
+            be.new_split_epoch()
+            if fused:
+                pred = net.forward(Tensor(x))
+            else:
+                pred = Tensor(x)
+                for layer in layers:
+                    pred = layer.forward(pred)
+            loss = SoftmaxCrossEntropyLoss().loss(pred, Tensor(labels))
+            loss.backward()
+            grads = [p.grad.copy() for layer in net.get_parameters() for p in layer.values()]
+            outs.append((pred.values.copy(), layers[1].inputs.values.copy(), layers[2].inputs.values.copy(), grads))
+        a, b = outs
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        for ga, gb in zip(a[3], b[3]):
+            assert np.array_equal(ga, gb)
+    finally:
+        be.TC_MIN_MNK = old
+
+
 def test_generic_step_path_equals_fused():
     """Model.step through compute_step()/`param += step` (the reference's three stages) gives the
     same parameters as the fused arena kernel"""

@@ -15,7 +15,7 @@ template <typename T, int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_t a_rs, int64_t a_cs,
                  const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                 const T* __restrict__ bias, int flags) {
+                 const T* __restrict__ bias, int flags, T* __restrict__ act_out) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_PER = (BM * BK) / NT;
   constexpr int B_PER = (BK * BN) / NT;
@@ -105,6 +105,7 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
       if (bias) v += bias[gn];
       if (accumulate) v += C[gm * ldc + gn];
       C[gm * ldc + gn] = v;
+      if (act_out) act_out[gm * ldc + gn] = v < T(0) ? T(0) : v;   // fused ReLU output
     }
   }
 }
@@ -112,7 +113,7 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
 template <typename T>
 static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
                           int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                          const T* bias, int flags) {
+                          const T* bias, int flags, T* act_out) {
   if (M <= 0 || N <= 0) return 0;
   cudaStream_t st = ctx().stream;
   prof_begin(2);
@@ -120,10 +121,10 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
   if (tiles64 >= ctx().sm_count) {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
     if (grid.y > 65535) TNN_FAIL("tnn_gemm_simt: M too large for the SIMT path");
-    gemm_simt_kernel<T, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags);
+    gemm_simt_kernel<T, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
   } else {
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
-    gemm_simt_kernel<T, 32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags);
+    gemm_simt_kernel<T, 32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
   }
   TNN_POST_LAUNCH();
   prof_end(2);
@@ -136,14 +137,14 @@ using namespace tnn;
 
 extern "C" int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs,
                              int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, int64_t M,
-                             int64_t N, int64_t K, const void* bias, int flags) {
+                             int64_t N, int64_t K, const void* bias, int flags, void* act_out) {
   TNN_REQUIRE_INIT();
   if (M < 0 || N < 0 || K < 0) TNN_FAIL("tnn_gemm_simt: negative extent");
   if (dtype == TNN_F32)
     return gemm_simt_impl<float>((float*)C, ldc, (const float*)A, a_rs, a_cs, (const float*)B, b_rs,
-                                 b_cs, M, N, K, (const float*)bias, flags);
+                                 b_cs, M, N, K, (const float*)bias, flags, (float*)act_out);
   if (dtype == TNN_F64)
     return gemm_simt_impl<double>((double*)C, ldc, (const double*)A, a_rs, a_cs, (const double*)B,
-                                  b_rs, b_cs, M, N, K, (const double*)bias, flags);
+                                  b_rs, b_cs, M, N, K, (const double*)bias, flags, (double*)act_out);
   TNN_FAIL("tnn_gemm_simt: dtype must be TNN_F32 or TNN_F64");
 }

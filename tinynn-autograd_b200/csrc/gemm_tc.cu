@@ -10,7 +10,7 @@
 //   tnn_gemm_tf32x3  D[M,N] = A[M,K] * B[N,K]^T.  Persistent, warp-specialised:
 //                      warp 0    TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier tx)
 //                      warp 1    MMA issuer    (tcgen05.mma.kind::tf32, 3 MMAs per K=8 step)
-//                      warps 2-9 epilogue      (tcgen05.ld TMEM -> fp32 regs (+=) -> bias/relu/accumulate)
+//                      warps 4-11 epilogue     (tcgen05.ld TMEM -> fp32 regs (+=) -> bias/relu/accumulate)
 //                    The tensor core accumulates in fp32 with round-toward-zero, which biases a long
 //                    K loop (measured: ~6e-5 relative at K = 4096).  So a TMEM accumulator only
 //                    ever holds a short chain (CHUNK_KB K blocks = 128 k): the 8 epilogue warps
@@ -39,7 +39,7 @@ constexpr int ROWS_A = 128;               // A rows staged per CTA
 constexpr int UMMA_N = 256;               // accumulator columns per tile
 constexpr int UMMA_K = 8;                 // tf32
 constexpr int PLANE_ROW_BYTES = BK * 4;   // 128
-constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
+constexpr int NUM_THREADS = 384;         // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1-2: epilogue
 constexpr int CHUNK_KB = 4;               // K blocks accumulated inside the tensor core per chunk
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -51,7 +51,8 @@ struct Cfg {
   static constexpr int B_BYTES = ROWS_B * PLANE_ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo of both operands
   static constexpr int TILE_M = ROWS_A * CG;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_PATCH_BYTES = 8 * 4096;                // one 32x32 fp32 patch per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_PATCH_BYTES;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -193,6 +194,12 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // Operand tiles in shared memory (one plane of one 32-wide K block, rows = 128 M/N rows):
 //   K-major  : one TMA box {32 k, rows}: row r at r*128 B, k contiguous, 128-byte swizzle.
 //              Descriptor: 8-row groups 1024 B apart (SBO); a K=8 step advances 32 B in the row.
@@ -243,7 +250,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_b_lo,
                    float* __restrict__ D, int64_t ldd, int M, int N, int K,
                    const float* __restrict__ bias, int flags, int t_full, int tail_split,
-                   unsigned int* __restrict__ tile_flags, int group_m) {
+                   unsigned int* __restrict__ tile_flags, int group_m,
+                   float* __restrict__ act_out, float* __restrict__ act_hi,
+                   float* __restrict__ act_lo, int64_t ld_act) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -315,8 +324,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
   };
 
+  // Register budget: the compiler is held to 168 registers per thread by the 384-thread block; the
+  // epilogue warps carry 128 fp32 tile sums each, so warpgroup 0 (TMA + MMA issue, a handful of
+  // registers) hands its share to warpgroups 1-2: 128*40 + 256*216 = 60,416 <= 65,536.
+  // (setmaxnreg sits inside each role branch so the compiler scopes the budget to that role.)
   if (warp == 0) {
     // ================= TMA producer =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -364,6 +378,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(C::TILE_M, UMMA_N, A_MN, B_MN);
       int stage = 0;
@@ -413,10 +428,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         }
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle warps of warpgroup 0
   } else {
     // ================= epilogue: TMEM chunks -> fp32 registers (RN adds) -> global =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
-    const int half = (warp - 2) >> 2;                // accumulator columns [128*half, 128*half+128)
+    const int half = (warp - 4) >> 2;                // accumulator columns [128*half, 128*half+128)
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool relu = flags & 2;
@@ -424,6 +442,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       int t, sp, kb_begin, kb_end;
       decode(u, t, sp, kb_begin, kb_end);
       const bool accumulate = (flags & 1) || sp > 0;
+      // the unit that holds the complete sum also emits the fused activation outputs
+      const bool emit_act = act_out != nullptr && (u < t_full || sp + 1 == tail_split);
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
       tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
@@ -474,37 +494,95 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         __syncwarp();
         __threadfence();
       }
-      if (row < M && col0 < N) {
-        float* drow = D + (int64_t)row * ldd;
-        if (col0 + 128 <= N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
+      // ---- store the tile.  A thread owns one row x 128 columns, so a direct store would touch 32
+      // rows with 16 bytes each per instruction (half-used sectors).  Each warp instead bounces its
+      // 32 x 32 blocks through a private 4 KB swizzled shared-memory patch and comes back with 8
+      // lanes per row: every global access is 4 full 128-byte lines.  While the epilogue warps are
+      // here the MMA issuer can only run two chunks ahead, so this phase has to be short.
+      {
+        const int row_base = tm * C::TILE_M + (int)cta_rank * ROWS_A + quad * 32;
+        float4* patch = reinterpret_cast<float4*>(smem_gen + C::STAGES * C::STAGE_BYTES + 256) +
+                        (warp - 4) * 256;                       // 32 rows x 8 float4
+        const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+        const bool act_aligned = !emit_act || ((reinterpret_cast<uintptr_t>(act_out) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 128; j += 4) {
-            float4 v = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+        for (int cb = 0; cb < 4; ++cb) {
+          const int colb = col0 + cb * 32;                      // first column of this 32-wide block
+          if (colb >= N) break;                                 // warp-uniform
+          // bias is per column: add it while the thread still owns consecutive columns
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 v = make_float4(sum[cb * 32 + c4 * 4], sum[cb * 32 + c4 * 4 + 1],
+                                   sum[cb * 32 + c4 * 4 + 2], sum[cb * 32 + c4 * 4 + 3]);
             if (bias_u) {
-              const float4 b = *reinterpret_cast<const float4*>(bias_u + col0 + j);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              const int c = colb + c4 * 4;
+              if (c + 3 < N) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_u + c);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              } else {
+                if (c < N) v.x += bias_u[c];
+                if (c + 1 < N) v.y += bias_u[c + 1];
+                if (c + 2 < N) v.z += bias_u[c + 2];
+              }
             }
-            if (accumulate) {
-              const float4 o = *reinterpret_cast<const float4*>(drow + col0 + j);
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            if (relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-              v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(drow + col0 + j) = v;
+            patch[lane * 8 + (c4 ^ (lane & 7))] = v;
           }
-        } else {
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            if (col0 + j < N) {
-              float v = sum[j];
-              if (bias_u) v += bias_u[col0 + j];
-              if (accumulate) v += drow[col0 + j];
-              if (relu) v = fmaxf(v, 0.f);
-              drow[col0 + j] = v;
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3), c4 = lane & 7;
+            float4 v = patch[r * 8 + (c4 ^ (r & 7))];
+            const int grow = row_base + r, gcol = colb + c4 * 4;
+            if (grow < M && gcol < N) {
+              float* dp = D + (int64_t)grow * ldd + gcol;
+              if (gcol + 3 < N && rows_aligned && act_aligned) {
+                if (accumulate) {
+                  const float4 o = *reinterpret_cast<const float4*>(dp);
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                if (relu) {
+                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                  v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(dp) = v;
+                if (emit_act) {
+                  // ReLU(D) (NaN-propagating like np.clip) and, optionally, its tf32 planes: the
+                  // next product consumes the activation without a separate relu / split pass
+                  const float4 a = make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y,
+                                               v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+                  *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = a;
+                  if (act_hi) {
+                    const float4 h = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+                    const float4 l = make_float4(to_tf32(a.x - h.x), to_tf32(a.y - h.y),
+                                                 to_tf32(a.z - h.z), to_tf32(a.w - h.w));
+                    *reinterpret_cast<float4*>(act_hi + (int64_t)grow * ld_act + gcol) = h;
+                    *reinterpret_cast<float4*>(act_lo + (int64_t)grow * ld_act + gcol) = l;
+                  }
+                }
+              } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (gcol + k < N) {
+                    float x = e[k];
+                    if (accumulate) x += dp[k];
+                    if (relu) x = fmaxf(x, 0.f);
+                    dp[k] = x;
+                    if (emit_act) {
+                      const float a = x < 0.f ? 0.f : x;
+                      act_out[(int64_t)grow * ldd + gcol + k] = a;
+                      if (act_hi) {
+                        const float h = to_tf32(a);
+                        act_hi[(int64_t)grow * ld_act + gcol + k] = h;
+                        act_lo[(int64_t)grow * ld_act + gcol + k] = to_tf32(a - h);
+                      }
+                    }
+                  }
+                }
+              }
             }
           }
+          __syncwarp();
         }
       }
       if (u >= t_full && sp + 1 < tail_split) {
@@ -529,11 +607,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 }
 
 // ---- fp32 -> tf32 hi/lo split (+ optional transposed copy) ----------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // 64 x 64 tile per CTA, 256 threads; plain planes are written with 128-bit stores straight from
 // registers, the transposed planes go through a padded shared-memory tile so both global sides
@@ -641,10 +714,17 @@ static int g_force_ksplit = 0;                 // 0 = auto (tail split), 1 = off
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3][2][2] = {};
 
+struct ActOut {
+  float* out = nullptr;   // relu(D), pitch ldd
+  float* hi = nullptr;    // tf32 planes of relu(D), pitch ld
+  float* lo = nullptr;
+  int64_t ld = 0;
+};
+
 template <int CG, bool A_MN, bool B_MN>
 static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                        const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
-                       int64_t K, const float* bias, int flags) {
+                       int64_t K, const float* bias, int flags, const ActOut& act) {
   using C = Cfg<CG>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (make_map(&ma_hi, a_hi, M, K, lda, ROWS_A, A_MN)) return 1;
@@ -703,7 +783,8 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(1);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m,
+                              act.out, act.hi, act.lo, act.ld));
   ctx().launches++;
   prof_end(1);
   return 0;
@@ -717,12 +798,13 @@ using namespace tnn;
 template <int CG>
 static int launch_by_layout(int layout, float* D, int64_t ldd, const float* a_hi, const float* a_lo,
                             int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, int64_t M,
-                            int64_t N, int64_t K, const float* bias, int flags) {
+                            int64_t N, int64_t K, const float* bias, int flags,
+                            const tnn::tc::ActOut& act) {
   switch (layout & 3) {
-    case 0: return tnn::tc::launch_gemm<CG, false, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
-    case 1: return tnn::tc::launch_gemm<CG, true, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
-    case 2: return tnn::tc::launch_gemm<CG, false, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
-    default: return tnn::tc::launch_gemm<CG, true, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    case 0: return tnn::tc::launch_gemm<CG, false, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+    case 1: return tnn::tc::launch_gemm<CG, true, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+    case 2: return tnn::tc::launch_gemm<CG, false, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+    default: return tnn::tc::launch_gemm<CG, true, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
   }
 }
 
@@ -766,7 +848,8 @@ int tnn_set_gemm_cta_group(int cg) {
 
 int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
-                    int64_t K, const float* bias, int flags, int layout) {
+                    int64_t K, const float* bias, int flags, int layout, float* act_out,
+                    float* act_hi, float* act_lo, int64_t ld_act) {
   TNN_REQUIRE_INIT();
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) TNN_FAIL("tnn_gemm_tf32x3: K must be positive");
@@ -780,10 +863,20 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
     if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
     env_read = true;
   }
+  tc::ActOut act;
+  if (act_out) {
+    if ((act_hi == nullptr) != (act_lo == nullptr)) TNN_FAIL("tnn_gemm_tf32x3: act_hi/act_lo come in pairs");
+    if (act_hi && (ld_act % 4 != 0 || ld_act < N)) TNN_FAIL("tnn_gemm_tf32x3: ld_act must be >= N and a multiple of 4");
+    if (flags & 2) TNN_FAIL("tnn_gemm_tf32x3: act_out and the relu-in-place flag are exclusive");
+    act.out = act_out;
+    act.hi = act_hi;
+    act.lo = act_lo;
+    act.ld = ld_act;
+  }
   int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
   if (cg == 2)
-    return launch_by_layout<2>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
-  return launch_by_layout<1>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags);
+    return launch_by_layout<2>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+  return launch_by_layout<1>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
 }
 
 }  // extern "C"
