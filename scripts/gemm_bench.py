@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--width", type=int, default=4096)
     ap.add_argument("--cg", default="1,2")
     ap.add_argument("--ksplit", default="0,1")
-    ap.add_argument("--group-m", default="1,4,8,16")
+    ap.add_argument("--group-m", default="1,-8,-4,1,-8,-4")
     args = ap.parse_args()
     be.init()
     B, D = args.batch, args.width

@@ -18,14 +18,14 @@ for s in $STAGES; do
     mnist) timeout 600 python bench.py --workload mnist --steps 200 --warmup 20 > gpurun_out/bench_mnist.log 2>&1 ;;
     sweep) timeout 900 python scripts/sweep_ops.py --cpu > gpurun_out/sweep.json 2> gpurun_out/sweep.err ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 22 -c 3 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1 ;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 22 -c 4 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1 ;;
     dist)  timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_dist.log 2>&1 ;;
     bench_n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.log 2>&1 ;;
     bench_n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/bench_n4.log 2>&1 ;;
     bench_n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/bench_n8.log 2>&1 ;;
     bench1) timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1 ;;
     memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_autograd_cases.py tests/test_gpu_gemm.py -m gpu -q -x -p no:cacheprovider > gpurun_out/memcheck.log 2>&1 ;;
-    gemmbench) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0,1 --group-m 1 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
+    gemmbench) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1,-8,-4,-2,1,-8,-4,-2 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
     ab_fuse) for i in 1 2 3; do TNN_FUSE_RELU=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse1.log 2>&1; TNN_FUSE_RELU=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse0.log 2>&1; done ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac

@@ -104,16 +104,29 @@ ew_flat_vec_kernel(T* out, const T* x, const T* y, const T* z, int64_t n, int sc
   T x0 = xs ? x[0] : T(0);
   T y0 = (AR >= 2 && ys) ? y[0] : T(0);
   T z0 = (AR >= 3 && zs) ? z[0] : T(0);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-    VecU<T, VEC> a, b, c, r;
-    if (!xs) a.v = reinterpret_cast<const V*>(x)[i];
-    if (AR >= 2 && !ys) b.v = reinterpret_cast<const V*>(y)[i];
-    if (AR >= 3 && !zs) c.v = reinterpret_cast<const V*>(z)[i];
+  constexpr int U = AR == 1 ? 4 : 2;   // independent vector loads in flight per operand and thread
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += U * stride) {
+    VecU<T, VEC> a[U], b[U], c[U], r;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      r.e[k] = ew_apply<OP, T>(xs ? x0 : a.e[k], (AR >= 2) ? (ys ? y0 : b.e[k]) : T(0),
-                               (AR >= 3) ? (zs ? z0 : c.e[k]) : T(0), p);
-    reinterpret_cast<V*>(out)[i] = r.v;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < nv) {
+        if (!xs) a[u].v = reinterpret_cast<const V*>(x)[i];
+        if (AR >= 2 && !ys) b[u].v = reinterpret_cast<const V*>(y)[i];
+        if (AR >= 3 && !zs) c[u].v = reinterpret_cast<const V*>(z)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < nv) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          r.e[k] = ew_apply<OP, T>(xs ? x0 : a[u].e[k], (AR >= 2) ? (ys ? y0 : b[u].e[k]) : T(0),
+                                   (AR >= 3) ? (zs ? z0 : c[u].e[k]) : T(0), p);
+        reinterpret_cast<V*>(out)[i] = r.v;
+      }
+    }
   }
   // tail (n not a multiple of VEC)
   int64_t t = nv * VEC + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -31,20 +31,39 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 template <typename T, bool BWD, bool VEC>
 __global__ void __launch_bounds__(256) relu_kernel(T* out, const T* g, const T* x, int64_t n) {
   constexpr int W = VEC ? V4<T>::W : 1;
+  constexpr int U = 4;   // independent 128-bit loads in flight per thread (a 1-read stream needs them)
   const int64_t nv = n / W;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += U * stride) {
     if constexpr (VEC) {
-      typename V4<T>::U a, b, r;
-      a.v = reinterpret_cast<const typename V4<T>::type*>(x)[i];
-      if (BWD) b.v = reinterpret_cast<const typename V4<T>::type*>(g)[i];
+      typename V4<T>::U a[U], b[U], r;
 #pragma unroll
-      for (int k = 0; k < W; ++k)
-        r.e[k] = BWD ? (a.e[k] >= T(0) ? b.e[k] : b.e[k] * T(0)) : m_max(a.e[k], T(0));
-      reinterpret_cast<typename V4<T>::type*>(out)[i] = r.v;
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < nv) {
+          a[u].v = reinterpret_cast<const typename V4<T>::type*>(x)[i];
+          if (BWD) b[u].v = reinterpret_cast<const typename V4<T>::type*>(g)[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < nv) {
+#pragma unroll
+          for (int k = 0; k < W; ++k)
+            r.e[k] = BWD ? (a[u].e[k] >= T(0) ? b[u].e[k] : b[u].e[k] * T(0)) : m_max(a[u].e[k], T(0));
+          reinterpret_cast<typename V4<T>::type*>(out)[i] = r.v;
+        }
+      }
     } else {
-      T a = x[i];
-      out[i] = BWD ? (a >= T(0) ? g[i] : g[i] * T(0)) : m_max(a, T(0));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < nv) {
+          T a = x[i];
+          out[i] = BWD ? (a >= T(0) ? g[i] : g[i] * T(0)) : m_max(a, T(0));
+        }
+      }
     }
   }
   if (VEC) {

@@ -232,6 +232,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 // 1-15 %, so 1 is the default and the knob stays for other shapes.
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm,
                                             int& tn) {
+  if (group_m < 0) {
+    // column panels: all tile rows of a panel of -group_m tile columns (row-major inside the panel)
+    // before the next panel, so the panel's B operand stays L2-resident across waves
+    const int gn = -group_m;
+    const int per_panel = tiles_m * gn;
+    const int g = t / per_panel;
+    const int first_n = g * gn;
+    const int cols = min(gn, tiles_n - first_n);
+    const int r = t - g * per_panel;
+    tm = r / cols;
+    tn = first_n + r % cols;
+    return;
+  }
   const int per_group = group_m * tiles_n;
   const int g = t / per_group;
   const int first_m = g * group_m;
@@ -829,7 +842,7 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C, float* hi, float* lo, i
 }
 
 int tnn_set_gemm_group_m(int gm) {
-  if (gm < 1 || gm > 64) TNN_FAIL("tnn_set_gemm_group_m: 1..64");
+  if (gm == 0 || gm > 64 || gm < -64) TNN_FAIL("tnn_set_gemm_group_m: 1..64 (row groups) or -1..-64 (column panels)");
   tc::g_group_m = gm;
   return 0;
 }
