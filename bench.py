@@ -102,6 +102,15 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def make_config(cfg, batch_per_gpu, world):
+    """the `config` object both arms print: the workload the metric is quoted on"""
+    return {"workload": cfg["name"], "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
+            "d_in": cfg["d_in"], "widths": cfg["widths"], "optimizer": "Adam(1e-3)",
+            "parallelism": "dp%d" % world,
+            "l2": "per-step working set (parameters, activations, tf32 planes) far exceeds the 126 MB L2 "
+                  "for the wide MLP; no flush between steps"}
+
+
 def gemm_flops_per_step(cfg, batch):
     """2*M*N*K over the forward, dX (all layers but the first) and dW products"""
     dims = [cfg["d_in"]] + cfg["widths"]
@@ -167,8 +176,7 @@ def run_reference_arm(args, cfg):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "batch_per_gpu": cfg["batch"], "sample_batch": sample,
-                   "optimizer": "Adam(1e-3)"},
+        "config": dict(make_config(cfg, cfg["batch"], args.gpus), sample_batch=sample),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -306,8 +314,14 @@ def run_b200_arm(args, cfg):
         per_launch_flops = flops_step * args.steps / gemm_n
         achieved = per_launch_flops / (gemm_ms / gemm_n * 1e-3) / 1e12
         peak = peaks["bf16_sustained"] / 6.0   # TF32 = bf16/2, three MMAs per algorithmic MMA
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):   # dram bytes per launch from the committed ncu --set full capture
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
+                    "frac_of_burst": achieved / (peaks["bf16_burst"] / 6.0),
+                    "frac_of_nominal_tf32": achieved / 375.0,
                     "kernel": "gemm_tf32x3_kernel", "launches": int(gemm_n),
                     "avg_launch_ms": gemm_ms / gemm_n, "share_of_step": gemm_ms / ms,
                     "peak_source": "%s bf16 sustained %.1f TFLOP/s / 6 (3xTF32)" % (
@@ -329,10 +343,7 @@ def run_b200_arm(args, cfg):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": cfg["name"], "batch_per_gpu": B, "global_batch": global_batch,
-                       "d_in": cfg["d_in"], "widths": cfg["widths"], "optimizer": "Adam(1e-3)",
-                       "parallelism": "dp%d" % world,
-                       "l2": "per-step working set (268 MB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
+            "config": make_config(cfg, B, world),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(B * (cfg["d_in"] + C) * 4), "d2h_bytes_per_step": 4,

@@ -266,6 +266,17 @@ def _as_index_array(key):
     return None
 
 
+def _last_writer(idx, modulus):
+    """numpy's `out[idx] = g` lets the LAST occurrence of a repeated index win.  A parallel scatter
+    would race, so repeated indices are resolved here: returns (unique indices, position of the
+    last occurrence of each) or None when every index is distinct."""
+    norm = np.where(idx < 0, idx + modulus, idx)
+    uniq, first_rev = np.unique(norm[::-1], return_index=True)
+    if uniq.size == norm.size:
+        return None
+    return uniq.astype(np.int64), (norm.size - 1 - first_rev).astype(np.int64)
+
+
 def getitem_(ts, key):
     """ops.py:282-290: x[key]; backward writes the gradient into zeros_like(x) at key
     (assignment, duplicates are not accumulated).
@@ -310,9 +321,14 @@ def getitem_(ts, key):
         n_idx = int(idx.size)
         idx_dev = be.upload_index(idx)
         values = be.gather_rows(x, idx_dev, n_idx)
+        dup = _last_writer(idx, shape[0]) if n_idx > 1 else None
 
         def grad_fn(grad):
-            return be.scatter_rows(grad, idx_dev, n_idx, shape)
+            if dup is None:
+                return be.scatter_rows(grad, idx_dev, n_idx, shape)
+            uniq, last = dup   # deterministic "last write wins", as numpy's assignment
+            winners = be.gather_rows(grad, be.upload_index(last), int(last.size))
+            return be.scatter_rows(winners, be.upload_index(uniq), int(uniq.size), shape)
 
         return build_unary_ops_tensor(ts, grad_fn, values)
     # general numpy key
@@ -322,11 +338,17 @@ def getitem_(ts, key):
         key = tuple(k.values if hasattr(k, "_data") else k for k in key)
     flat = np.arange(x.size, dtype=np.int64).reshape(shape)[key]
     oshape = flat.shape
-    idx_dev = be.upload_index(np.ascontiguousarray(flat).ravel())
+    flat_idx = np.ascontiguousarray(flat).ravel()
+    idx_dev = be.upload_index(flat_idx)
     values = be.gather_flat(x, idx_dev, oshape)
+    dup = _last_writer(flat_idx, x.size) if flat_idx.size > 1 else None
 
     def grad_fn(grad):
-        return be.scatter_flat(grad, idx_dev, shape)
+        if dup is None:
+            return be.scatter_flat(grad, idx_dev, shape)
+        uniq, last = dup
+        winners = be.gather_flat(grad.view((grad.size,)), be.upload_index(last), (int(last.size),))
+        return be.scatter_flat(winners, be.upload_index(uniq), shape)
 
     return build_unary_ops_tensor(ts, grad_fn, values)
 

@@ -78,6 +78,27 @@ def test_shape_and_stride_helpers(built_lib):
     assert be._round4(70) == 72
 
 
+def test_duplicate_index_scatter_resolution():
+    """getitem_ backward is an assignment (ops.py:285-288): numpy lets the last occurrence of a
+    repeated index win; the host resolves that before the (parallel) scatter kernel runs"""
+    import core.ops as ops
+    rng = np.random.RandomState(0)
+    for n, m in ((5, 9), (40, 7), (1000, 50)):
+        idx = rng.randint(-m, m, n)
+        g = rng.standard_normal(n)
+        ref = np.zeros(m)
+        ref[idx] = g
+        res = ops._last_writer(idx, m)
+        out = np.zeros(m)
+        if res is None:
+            out[np.where(idx < 0, idx + m, idx)] = g
+        else:
+            uniq, last = res
+            out[uniq] = g[last]
+        assert np.array_equal(out, ref)
+    assert ops._last_writer(np.array([3, 1, 2]), 5) is None
+
+
 def test_shard_bounds_and_stats_merge():
     import core._dist as dist
     for n, w in ((65536, 8), (10, 3), (7, 8)):
