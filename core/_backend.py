@@ -105,7 +105,8 @@ _SIGNATURES = {
     "tnn_allgather": [_c_int, _c_vp, _c_vp, _c_i64],
     "tnn_nccl_version": [_c_vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["tnn_last_error", "tnn_stream", "tnn_launch_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["tnn_last_error", "tnn_stream", "tnn_launch_count",
+                                                "tnn_alloc_ptr"])
 
 
 def load_library():
@@ -128,6 +129,8 @@ def load_library():
     lib.tnn_stream.restype = _c_vp
     lib.tnn_launch_count.argtypes = []
     lib.tnn_launch_count.restype = ctypes.c_uint64
+    lib.tnn_alloc_ptr.argtypes = [_c_sz]
+    lib.tnn_alloc_ptr.restype = _c_vp
     _lib = lib
     return lib
 
@@ -189,10 +192,10 @@ class _Buf(object):
     __slots__ = ("ptr", "nbytes", "__weakref__")
 
     def __init__(self, nbytes):
-        out = _c_vp()
-        if _lib.tnn_alloc(nbytes, ctypes.byref(out)):
+        ptr = _lib.tnn_alloc_ptr(nbytes)
+        if not ptr:
             _raise("tnn_alloc")
-        self.ptr = out.value
+        self.ptr = ptr
         self.nbytes = nbytes
 
     def __del__(self):
@@ -260,10 +263,16 @@ def device_dtype(np_dtype):
 
 
 def empty(shape, dtype):
-    init()
-    shape = tuple(int(s) for s in shape)
-    dtype = np.dtype(dtype)
-    buf = _Buf(max(_prod(shape), 1) * dtype.itemsize)
+    if not _inited:
+        init()
+    if type(shape) is not tuple:
+        shape = tuple(int(s) for s in shape)
+    if type(dtype) is not np.dtype:
+        dtype = np.dtype(dtype)
+    n = 1
+    for s in shape:
+        n *= s
+    buf = _Buf((n if n > 0 else 1) * dtype.itemsize)
     return DArray(buf, buf.ptr, shape, dtype)
 
 

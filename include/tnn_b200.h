@@ -90,6 +90,7 @@ uint64_t tnn_launch_count(void);          /* number of kernels this library has 
 
 /* ---- memory: stream-ordered caching pool (replaces numpy's implicit malloc) ---------------- */
 int tnn_alloc(size_t nbytes, void** out);
+void* tnn_alloc_ptr(size_t nbytes);       /* same, returns the pointer; NULL on failure */
 int tnn_free(void* p);
 int tnn_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* n_cuda_malloc);
 int tnn_pool_trim(void);

@@ -123,8 +123,11 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
     if (grid.y > 65535) TNN_FAIL("tnn_gemm_simt: M too large for the SIMT path");
     gemm_simt_kernel<T, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
   } else {
+    // few CTAs: the K loop is a chain of exposed global-load latencies (measured 53 us for the
+    // 128x200x784 first MNIST layer with 16-wide K slabs), so the small-tile variant takes 64-wide
+    // slabs: 4x fewer round trips, 8 loads in flight per thread
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
-    gemm_simt_kernel<T, 32, 32, 16, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
+    gemm_simt_kernel<T, 32, 32, 64, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
   }
   TNN_POST_LAUNCH();
   prof_end(2);

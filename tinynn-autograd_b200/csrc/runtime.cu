@@ -228,6 +228,14 @@ int tnn_alloc(size_t nbytes, void** out) {
   return 0;
 }
 
+// same as tnn_alloc, returning the pointer (NULL on failure): one scalar argument, no out-parameter,
+// which halves the host cost of the call that every op result goes through
+void* tnn_alloc_ptr(size_t nbytes) {
+  void* p = nullptr;
+  if (tnn_alloc(nbytes, &p)) return nullptr;
+  return p;
+}
+
 int tnn_free(void* p) {
   if (!p) return 0;
   std::lock_guard<std::mutex> lk(g_pool.mu);
