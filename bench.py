@@ -232,17 +232,17 @@ def run_b200_arm(args, cfg):
     x_dev = [be.from_numpy(x_host.array[k]) for k in range(2)]
     y_dev = [be.from_numpy(y_host.array[k]) for k in range(2)]
 
-    def train_step(xd, yd):
+    def train_step(x_t, y_t):
         model.zero_grad()
-        pred = model.forward(Tensor(xd))
-        loss = loss_layer.loss(pred, Tensor(yd))
+        pred = model.forward(x_t)
+        loss = loss_layer.loss(pred, y_t)
         loss.backward()
         model.step()
         return loss
 
     # ---- device-resident throughput ("value") --------------------------------------------------
     for i in range(args.warmup):
-        loss = train_step(x_dev[i % 2], y_dev[i % 2])
+        loss = train_step(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
     float(loss.values)
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -252,7 +252,7 @@ def run_b200_arm(args, cfg):
     ev0, ev1 = be.Event(), be.Event()
     ev0.record()
     for i in range(args.steps):
-        loss = train_step(x_dev[i % 2], y_dev[i % 2])
+        loss = train_step(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
     ev1.record()
     dist.barrier()
     ms = ev1.elapsed_ms_since(ev0)
@@ -262,38 +262,35 @@ def run_b200_arm(args, cfg):
     clocks = sampler.stop()
     last_loss = float(loss.values)
 
-    # ---- end to end from host buffers ("e2e") --------------------------------------------------
-    xe = [be.empty((B, cfg["d_in"]), be.F32) for _ in range(2)]
-    ye = [be.empty((B, C), be.F32) for _ in range(2)]
-    xp = [be.PinnedArray((B, cfg["d_in"]), np.float32) for _ in range(2)]
-    yp = [be.PinnedArray((B, C), np.float32) for _ in range(2)]
-    for k in range(2):
-        xp[k].array[...] = x_host.array[k]
-        yp[k].array[...] = y_host.array[k]
-
-    def prefetch(k):
-        be.h2d_prefetch(xe[k], xp[k])
-        be.h2d_prefetch(ye[k], yp[k])
-
+    # ---- end to end from host buffers ("e2e"): the public input pipeline ----------------------
+    # utils.data_iterator.PrefetchIterator over a host data set of 4 batches (pinned in place):
+    # batch i+1 is DMA'd on the copy stream while step i runs; the loss is read back every step.
+    from utils.data_iterator import PrefetchIterator
+    n_host_batches = 4
+    x_data = np.empty((n_host_batches * B, cfg["d_in"]), np.float32)
+    y_data = np.zeros((n_host_batches * B, C), np.float32)
+    for k in range(n_host_batches):
+        x_data[k * B:(k + 1) * B] = x_host.array[k % 2]
+        y_data[k * B:(k + 1) * B] = y_host.array[(k + 1) % 2]
+    del x_host, y_host
     e2e_steps = args.steps
-    prefetch(0)
-    for i in range(2):                                   # e2e warm-up
-        be.wait_prefetch()
-        prefetch((i + 1) % 2)
-        float(train_step(xe[i % 2], ye[i % 2]).values)
+    feed = iter(PrefetchIterator(batch_size=B, loop=True)(x_data, y_data))
+    for _ in range(2):                                   # e2e warm-up
+        batch = next(feed)
+        float(train_step(batch.inputs, batch.targets).values)
     dist.barrier()
     t0 = time.perf_counter()
     e0, e1 = be.Event(), be.Event()
     e0.record()
-    for i in range(e2e_steps):
-        be.wait_prefetch()                               # batch i has landed
-        prefetch((i + 1) % 2)                            # batch i+1 copies while step i computes
-        float(train_step(xe[i % 2], ye[i % 2]).values)   # D2H read of the loss every step
+    for _ in range(e2e_steps):
+        batch = next(feed)                               # H2D of the NEXT batch is queued in here
+        float(train_step(batch.inputs, batch.targets).values)   # D2H read of the loss
     e1.record()
     dist.barrier()
     e2e_ms = e1.elapsed_ms_since(e0)
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e2e_ms, e2e_wall)
+    feed.close()
 
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:

@@ -59,7 +59,10 @@ _SIGNATURES = {
     "tnn_memset": [_c_vp, _c_int, _c_sz],
     "tnn_host_alloc": [_c_sz, _c_vp],
     "tnn_host_free": [_c_vp],
+    "tnn_host_register": [_c_vp, _c_sz],
+    "tnn_host_unregister": [_c_vp],
     "tnn_h2d_async_copy_stream": [_c_vp, _c_vp, _c_sz],
+    "tnn_copy_stream_sync": [],
     "tnn_copy_wait_compute": [],
     "tnn_compute_wait_copy": [],
     "tnn_event_create": [_c_vp],
@@ -797,12 +800,45 @@ class PinnedArray(object):
             pass
 
 
+class RegisteredHostArray(object):
+    """a caller-owned C-contiguous numpy array pinned in place (cudaHostRegister) for the lifetime
+    of this object"""
+
+    def __init__(self, array):
+        init()
+        if not (isinstance(array, np.ndarray) and array.flags["C_CONTIGUOUS"]):
+            raise ValueError("only C-contiguous numpy arrays can be pinned in place")
+        self.array = array
+        self.ptr = array.ctypes.data
+        if _lib.tnn_host_register(self.ptr, array.nbytes):
+            _raise("tnn_host_register")
+
+    def row_address(self, row):
+        return self.ptr + row * self.array.strides[0]
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.tnn_host_unregister(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 def h2d_prefetch(dst, pinned):
-    """queue pinned -> dst on the copy stream, after everything queued so far on compute"""
+    """queue pinned -> dst on the copy stream, after everything queued so far on compute.
+    `pinned` is a PinnedArray / RegisteredHostArray or a raw address inside pinned memory."""
     if _lib.tnn_copy_wait_compute():
         _raise("tnn_copy_wait_compute")
-    if _lib.tnn_h2d_async_copy_stream(dst.ptr, pinned.ptr, dst.nbytes):
+    src = pinned if isinstance(pinned, int) else pinned.ptr
+    if _lib.tnn_h2d_async_copy_stream(dst.ptr, src, dst.nbytes):
         _raise("tnn_h2d_async_copy_stream")
+
+
+def copy_stream_sync():
+    """host waits for the copy stream: a pinned staging buffer may be rewritten afterwards"""
+    if _lib.tnn_copy_stream_sync():
+        _raise("tnn_copy_stream_sync")
 
 
 def wait_prefetch():

@@ -1,8 +1,20 @@
-"""Loss functions (interface of the reference's core/losses.py)."""
+"""Loss functions (interface of the reference's core/losses.py: BaseLoss, SoftmaxCrossEntropyLoss).
+
+The reference's softmax cross-entropy is unusual and the engine reproduces it exactly: the maximum
+that is subtracted and the sum that normalises the exponentials are taken over the WHOLE
+batch x class matrix (losses.py:26-27 call .max() and .sum() without an axis), so
+
+    p_ij = exp(z_ij - max z) / sum_kl exp(z_kl - max z)
+    L    = -(1/m) sum_i log( sum_j p_ij * labels_ij )
+
+and the initial loss of an untrained classifier is about log(m * C), not log(C).  The fused node
+(ops.softmax_ce_) computes this with three streaming passes forward and one backward; under data
+parallelism the max / sum pair is merged across ranks so the normaliser still spans the global
+batch.
+"""
 import numpy as np
 
 import core.ops as ops
-from core.tensor import Tensor
 from core.tensor import as_tensor
 
 
@@ -15,30 +27,29 @@ class BaseLoss(object):
 class SoftmaxCrossEntropyLoss(BaseLoss):
 
     def __init__(self, weight=None):
-        """
-        L = -(1/m) sum_i log( sum_j p_ij * labels_ij ),  p = exp(x - max(x)) / sum(exp(x - max(x)))
-        where, as in the reference (losses.py:26-27), max and sum run over the WHOLE batch x
-        class matrix.  `weight` is accepted for signature compatibility; the reference's weighted
-        path indexes a numpy array with a Tensor and cannot run, so it is rejected here.
-        """
-        weight = np.asarray(weight) if weight is not None else weight
-        self._weight = weight
+        # `weight` ([n_classes]) is part of the reference signature; its weighted path indexes a
+        # numpy array with a one-hot Tensor (losses.py:30-31) and cannot execute, so a weight is
+        # accepted here only to be refused at call time with a clear message.
+        self._weight = None if weight is None else np.asarray(weight)
 
     def loss(self, logits, labels):
         if self._weight is not None:
-            raise NotImplementedError("class weights are not supported (broken upstream, losses.py:30-31)")
-        logits = as_tensor(logits)
-        labels = as_tensor(labels)
-        if logits.ndim == 2 and labels.shape == logits.shape:
-            return ops.softmax_ce_(logits, labels)  # one fused node
-        return self.loss_composed(logits, labels)
+            raise NotImplementedError(
+                "class weights are not supported (the reference's weighted path is broken, "
+                "losses.py:30-31)")
+        z, y = as_tensor(logits), as_tensor(labels)
+        fused_ok = z.ndim == 2 and tuple(y.shape) == tuple(z.shape)
+        return ops.softmax_ce_(z, y) if fused_ok else self.loss_composed(z, y)
 
     @staticmethod
     def loss_composed(logits, labels):
-        """The same expression written with the primitive ops, line for line losses.py:25-32.
-        Used for shapes the fused kernel does not take and by the tests as a cross-check."""
-        m = logits.shape[0]
-        exps = ops.exp(logits - logits.max())
-        p = exps / exps.sum()
-        nll = -ops.log((p * labels).sum(1))
-        return nll.sum() / m
+        """The same quantity assembled from the primitive differentiable ops (eleven graph nodes,
+        the way losses.py:25-32 builds it).  Serves shapes the fused kernel does not take and is
+        the cross-check the test-suite runs against the fused node."""
+        batch = logits.shape[0]
+        shifted = ops.sub_(logits, ops.max_(logits, axis=None))        # z - max(z), global max
+        unnormalised = ops.exp_(shifted)
+        probs = ops.div_(unnormalised, ops.sum_(unnormalised, axis=None))   # global normaliser
+        picked = ops.sum_(ops.mul_(probs, as_tensor(labels)), axis=1)   # q_i = sum_j p_ij y_ij
+        total = ops.sum_(ops.neg_(ops.log_(picked)), axis=None)
+        return total / batch

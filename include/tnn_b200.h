@@ -100,8 +100,11 @@ int tnn_d2d(void* dst, const void* src, size_t nbytes);
 int tnn_memset(void* dst, int byte, size_t nbytes);
 int tnn_host_alloc(size_t nbytes, void** out);            /* pinned host memory */
 int tnn_host_free(void* p);
+int tnn_host_register(void* p, size_t nbytes);            /* pin caller-owned host memory in place */
+int tnn_host_unregister(void* p);
 /* copy-stream plumbing for input prefetch (run.py:78 batches overlap the previous step) */
 int tnn_h2d_async_copy_stream(void* dst, const void* pinned_src, size_t nbytes);
+int tnn_copy_stream_sync(void);           /* host waits until queued copies are done (staging reuse) */
 int tnn_copy_wait_compute(void);          /* copy stream waits for work queued so far on compute */
 int tnn_compute_wait_copy(void);          /* compute stream waits for copies queued so far       */
 /* events on the compute stream (bench timing) */

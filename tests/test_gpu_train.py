@@ -296,3 +296,29 @@ def test_save_load_roundtrip(tmp_path):
     model2.forward(x)
     model2.load(path)
     assert np.array_equal(model2.forward(x).values, y0)
+
+
+def test_prefetch_iterator_delivers_the_right_rows():
+    """utils.data_iterator.PrefetchIterator: host data set -> device batches over the copy stream
+    (pinned in place without shuffling, staged with shuffling); every batch must hold exactly the
+    rows the equivalent numpy indexing gives, including the short last batch and loop mode"""
+    from utils.data_iterator import PrefetchIterator
+    rng = np.random.RandomState(0)
+    x = rng.rand(1000, 37).astype(np.float32)
+    y = rng.rand(1000, 5).astype(np.float32)
+    got = [(b.inputs.values.copy(), b.targets.values.copy()) for b in PrefetchIterator(batch_size=128)(x, y)]
+    assert [len(a) for a, _ in got] == [128] * 7 + [104]
+    assert np.array_equal(np.concatenate([a for a, _ in got]), x)
+    assert np.array_equal(np.concatenate([b for _, b in got]), y)
+    np.random.seed(5)
+    got = [(b.inputs.values.copy(), b.targets.values.copy())
+           for b in PrefetchIterator(batch_size=128, shuffle=True)(x, y)]
+    np.random.seed(5)
+    order = np.arange(1000)
+    np.random.shuffle(order)
+    assert np.array_equal(np.concatenate([a for a, _ in got]), x[order])
+    assert np.array_equal(np.concatenate([b for _, b in got]), y[order])
+    feed = iter(PrefetchIterator(batch_size=400, loop=True)(x, y))
+    sizes = [len(next(feed).inputs) for _ in range(7)]
+    assert sizes == [400, 400, 200, 400, 400, 200, 400]
+    feed.close()

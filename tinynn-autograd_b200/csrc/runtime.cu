@@ -309,10 +309,30 @@ int tnn_host_free(void* p) {
   return 0;
 }
 
+// pin / unpin caller-owned host memory in place, so batches can be DMA'd straight out of a numpy
+// data set without a staging copy
+int tnn_host_register(void* p, size_t nbytes) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaHostRegister(p, nbytes, cudaHostRegisterDefault));
+  return 0;
+}
+
+int tnn_host_unregister(void* p) {
+  if (!p || !ctx().inited) return 0;
+  TNN_CUDA(cudaHostUnregister(p));
+  return 0;
+}
+
 int tnn_h2d_async_copy_stream(void* dst, const void* pinned_src, size_t nbytes) {
   TNN_REQUIRE_INIT();
   if (nbytes == 0) return 0;
   TNN_CUDA(cudaMemcpyAsync(dst, pinned_src, nbytes, cudaMemcpyHostToDevice, ctx().copy_stream));
+  return 0;
+}
+
+int tnn_copy_stream_sync(void) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaStreamSynchronize(ctx().copy_stream));
   return 0;
 }
 

@@ -1,7 +1,13 @@
-"""Mini-batch iterator (interface of the reference's utils/data_iterator.py).
+"""Mini-batch iterators.
 
-Works on numpy arrays and on device Tensors alike: the per-epoch shuffle `inputs[idx]` is one
-row-gather kernel on a Tensor, the per-step `inputs[start:end]` a zero-copy view.
+BatchIterator keeps the reference's interface (utils/data_iterator.py): called with (inputs,
+targets) it yields Batch(inputs, targets) namedtuples, reshuffling once per call with numpy's
+global generator.  On device Tensors the shuffle is ONE row-gather kernel and every mini-batch is a
+zero-copy row view (the two getitem patterns of SURVEY 8a/a21); on numpy arrays it is plain
+indexing.
+
+PrefetchIterator is the host-fed variant: the data set stays in (pinned) host memory and batch
+i+1 is copied to the GPU on the copy stream while batch i trains, double-buffered.
 """
 from collections import namedtuple
 
@@ -16,6 +22,11 @@ class BaseIterator(object):
         raise NotImplementedError
 
 
+def _batch_bounds(n_rows, batch_size):
+    """[(start, stop)] covering n_rows; the last batch may be short (50000 = 390*128 + 80)"""
+    return [(lo, min(lo + batch_size, n_rows)) for lo in range(0, n_rows, batch_size)]
+
+
 class BatchIterator(BaseIterator):
 
     def __init__(self, batch_size=32, shuffle=True):
@@ -23,11 +34,92 @@ class BatchIterator(BaseIterator):
         self.shuffle = shuffle
 
     def __call__(self, inputs, targets):
-        n = len(inputs)
+        n_rows = len(inputs)
         if self.shuffle:
-            order = np.arange(n)
-            np.random.shuffle(order)  # same RNG call as data_iterator.py:25-26
+            order = np.arange(n_rows)
+            np.random.shuffle(order)            # the reference's RNG call (data_iterator.py:25-26)
             inputs, targets = inputs[order], targets[order]
-        for start in range(0, n, self.batch_size):
-            stop = start + self.batch_size
-            yield Batch(inputs=inputs[start:stop], targets=targets[start:stop])
+        for lo, hi in _batch_bounds(n_rows, self.batch_size):
+            yield Batch(inputs=inputs[lo:hi], targets=targets[lo:hi])
+
+
+class PrefetchIterator(BaseIterator):
+    """Yields device-Tensor batches from HOST float32 arrays, with the H2D copy of batch i+1
+    overlapping the step on batch i.
+
+        it = PrefetchIterator(batch_size=8192)
+        for batch in it(x_host, y_host):      # numpy arrays; rows are sharded by the caller
+            ...train on batch.inputs / batch.targets ...
+
+    Without shuffling the data set is pinned in place (cudaHostRegister) and every batch is DMA'd
+    straight out of it; with shuffling the rows of a batch are first gathered into a pinned staging
+    buffer.  Two device buffers per stream of data: a buffer is rewritten two iterations later,
+    after the compute stream has passed the kernels that read it.  loop=True wraps around
+    indefinitely (the caller breaks)."""
+
+    def __init__(self, batch_size=32, shuffle=False, loop=False):
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.loop = loop
+        self._cache = None
+
+    def _buffers(self, inputs, targets):
+        import core._backend as be
+        key = (id(inputs), id(targets), self.batch_size, self.shuffle)
+        if self._cache is not None and self._cache["key"] == key:
+            return self._cache
+        xs = (self.batch_size,) + tuple(inputs.shape[1:])
+        ys = (self.batch_size,) + tuple(targets.shape[1:])
+        cache = {"key": key, "dev": [(be.empty(xs, be.F32), be.empty(ys, be.F32)) for _ in range(2)]}
+        if self.shuffle:
+            cache["stage"] = [(be.PinnedArray(xs, np.float32), be.PinnedArray(ys, np.float32))
+                              for _ in range(2)]
+        else:
+            cache["pinned"] = (be.RegisteredHostArray(inputs), be.RegisteredHostArray(targets))
+        self._cache = cache
+        return cache
+
+    def __call__(self, inputs, targets):
+        import core._backend as be
+        from core.tensor import Tensor
+        inputs = np.require(inputs, np.float32, "C")
+        targets = np.require(targets, np.float32, "C")
+        n_rows = len(inputs)
+        bounds = _batch_bounds(n_rows, self.batch_size)
+        if not bounds:
+            return
+        buf = self._buffers(inputs, targets)
+        order = np.arange(n_rows)
+
+        def stage(step):
+            lo, hi = bounds[step % len(bounds)]
+            n = hi - lo
+            x_dev, y_dev = buf["dev"][step % 2]
+            xv, yv = x_dev.view((n,) + x_dev.shape[1:]), y_dev.view((n,) + y_dev.shape[1:])
+            if self.shuffle:
+                if step % len(bounds) == 0:
+                    np.random.shuffle(order)
+                x_pin, y_pin = buf["stage"][step % 2]
+                be.copy_stream_sync()               # the previous copy out of this staging pair is done
+                x_pin.array[:n] = inputs[order[lo:hi]]
+                y_pin.array[:n] = targets[order[lo:hi]]
+                be.h2d_prefetch(xv, x_pin)
+                be.h2d_prefetch(yv, y_pin)
+            else:
+                px, py = buf["pinned"]
+                be.h2d_prefetch(xv, px.row_address(lo))
+                be.h2d_prefetch(yv, py.row_address(lo))
+            return xv, yv
+
+        step = 0
+        pending = stage(0)
+        while True:
+            be.wait_prefetch()                       # batch `step` is on the device
+            xv, yv = pending
+            last = (not self.loop) and step + 1 >= len(bounds)
+            if not last:
+                pending = stage(step + 1)            # overlaps with the caller's work on this batch
+            yield Batch(inputs=Tensor(xv), targets=Tensor(yv))
+            if last:
+                return
+            step += 1
