@@ -89,7 +89,7 @@ _SIGNATURES = {
                       _c_i64, _c_i64, _c_vp, _c_int, _c_vp],
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
-                        _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64],
+                        _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "tnn_set_gemm_cta_group": [_c_int],
     "tnn_set_gemm_ksplit": [_c_int],
     "tnn_set_gemm_group_m": [_c_int],
@@ -218,7 +218,7 @@ def _prod(shape):
 
 class DArray(object):
     """Contiguous row-major device array (float32 or float64)."""
-    __slots__ = ("buf", "ptr", "shape", "dtype", "size", "split", "__weakref__")
+    __slots__ = ("buf", "ptr", "shape", "dtype", "size", "split", "aux", "__weakref__")
 
     def __init__(self, buf, ptr, shape, dtype):
         self.buf = buf
@@ -227,6 +227,7 @@ class DArray(object):
         self.dtype = dtype
         self.size = _prod(shape)
         self.split = None  # tf32 hi/lo planes cache, see split_planes()
+        self.aux = None    # (pre-activation, masked gradient) left by a fused dX epilogue
 
     @property
     def ndim(self):
@@ -638,7 +639,7 @@ def use_tensor_cores(M, N, K, dtype):
 
 
 def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu=False,
-           reuse_a=False, reuse_b=False, act=False):
+           reuse_a=False, reuse_b=False, act=False, mask_src=None):
     """op(a) @ op(b) (+ bias) for 2-D arrays; op = transpose when ta/tb (ops.py:150-160).
 
     float32 products above TC_MIN_MNK run on the tcgen05 3xTF32 kernel; float64 and small or
@@ -648,7 +649,9 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
 
     act=True returns (out, relu(out)): the GEMM epilogue writes the ReLU of its result as a second
     array -- and, on the tensor-core path, that array's tf32 planes, which are attached to it so the
-    next product consumes it without a separate ReLU or split pass."""
+    next product consumes it without a separate ReLU or split pass.  With mask_src (the
+    pre-activation of the ReLU that produced op(b)'s counterpart) the second array is instead
+    out * (mask_src >= 0): the ReLU backward fused into the dX product."""
     if a.ndim != 2 or b.ndim != 2:
         raise ValueError("matmul: only 2-D operands are supported (got %s @ %s)" % (a.shape, b.shape))
     dt = _common_dtype(a, b)
@@ -688,7 +691,8 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         if _lib.tnn_gemm_tf32x3(out.ptr, N, a_hi.ptr, a_lo.ptr, lda, b_hi.ptr, b_lo.ptr, ldb, M, N,
                                 K, bias.ptr if bias is not None else None, flags, layout,
                                 act_out.ptr if act else None, act_hi.ptr if act else None,
-                                act_lo.ptr if act else None, ld_act):
+                                act_lo.ptr if act else None, ld_act,
+                                mask_src.ptr if (act and mask_src is not None) else None):
             _raise("tnn_gemm_tf32x3")
         if act:
             act_out.split = {"epoch": _split_epoch, "p": (act_hi, act_lo, ld_act)}
@@ -696,10 +700,14 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         return out
     a_rs, a_cs = (1, a.shape[1]) if ta else (a.shape[1], 1)
     b_rs, b_cs = (1, b.shape[1]) if tb else (b.shape[1], 1)
+    fused_act = act and mask_src is None
     if _lib.tnn_gemm_simt(_DT_CODE[dt], out.ptr, N, a.ptr, a_rs, a_cs, b.ptr, b_rs, b_cs, M, N, K,
                           bias.ptr if bias is not None else None, flags & 1,
-                          act_out.ptr if act else None):
+                          act_out.ptr if fused_act else None):
         _raise("tnn_gemm_simt")
+    if act and mask_src is not None:   # SIMT path: the mask is a separate (tiny) launch
+        if _lib.tnn_relu_bwd(_DT_CODE[dt], act_out.ptr, out.ptr, mask_src.ptr, out.size):
+            _raise("tnn_relu_bwd")
     if relu:
         if _lib.tnn_relu_fwd(_DT_CODE[dt], out.ptr, out.ptr, out.size):
             _raise("tnn_relu_fwd")

@@ -47,6 +47,7 @@ class Tensor(object):
         self._grad_zero = False  # True = "gradient is all zeros" without having allocated it
         self._grad_host = None
         self._gslot = None       # view into a flat gradient arena (set by core.model.Model)
+        self._relu_pre = None    # pre-activation array when this tensor is a fused ReLU output
         self.requires_grad = requires_grad
         if self.requires_grad:
             self.zero_grad()

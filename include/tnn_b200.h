@@ -172,12 +172,16 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C,
  * Fused activation outputs (Dense -> ReLU -> next Dense without extra passes, layers.py:49,97-98):
  * act_out (may be NULL, pitch ldd) receives ReLU(D) while D keeps the pre-activation the ReLU
  * backward mask needs; act_hi/act_lo (may be NULL, pitch ld_act) receive the tf32 planes of
- * ReLU(D), i.e. the A operand of the next layer's product. */
+ * ReLU(D), i.e. the A operand of the next layer's product.
+ * Backward form: with mask_src (pitch ldd) set, act_out = D * (mask_src >= 0) instead -- the dX
+ * product of a layer whose input came out of a ReLU hands back both dL/da (D) and dL/dz (act_out,
+ * with tf32 planes for the dW / dX products it feeds), ops.py:342-343 fused into ops.py:156-157. */
 int tnn_gemm_tf32x3(float* D, int64_t ldd,
                     const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb,
                     int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout,
-                    float* act_out, float* act_hi, float* act_lo, int64_t ld_act);
+                    float* act_out, float* act_hi, float* act_lo, int64_t ld_act,
+                    const float* mask_src);
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);

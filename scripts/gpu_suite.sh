@@ -28,6 +28,7 @@ for s in $STAGES; do
     gemmbench) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1,-8,-4,-2,1,-8,-4,-2 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
     ab_fuse) for i in 1 2 3; do TNN_FUSE_RELU=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse1.log 2>&1; TNN_FUSE_RELU=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse0.log 2>&1; done ;;
     ncu_mnist) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv --log-file gpurun_out/launches_mnist.csv python bench.py --workload mnist --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/ncu_mnist.log 2>&1 ;;
+    ab_bwd) for i in 1 2 3; do TNN_FUSE_RELU_BWD=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd1.log 2>&1; TNN_FUSE_RELU_BWD=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd0.log 2>&1; done ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt

@@ -218,12 +218,14 @@ def test_tensor_core_mlp_step_teacher_forced(cg):
         be.set_gemm_cta_group(0)
 
 
+@pytest.mark.parametrize("fuse_bwd", [False, True])
 @pytest.mark.parametrize("size", [(16, 20, 12, 8), (512, 256, 384, 128)])
-def test_dense_relu_fusion_is_transparent(size):
+def test_dense_relu_fusion_is_transparent(size, fuse_bwd):
     """Net.forward runs Dense+ReLU as one GEMM launch (ReLU and the next layer's tf32 planes come
     out of the epilogue); values, recorded layer inputs and every gradient are bit-identical to
     calling the layers one by one (small = SIMT kernel, large = tcgen05 kernel)"""
     import core._backend as be
+    import core.ops as ops
     from core.layers import Dense, ReLU
     from core.losses import SoftmaxCrossEntropyLoss
     from core.nn import Net
@@ -233,7 +235,9 @@ def test_dense_relu_fusion_is_transparent(size):
     x = rng.standard_normal((B, D)).astype(np.float32)
     labels = np.eye(C, dtype=np.float32)[rng.randint(0, C, B)]
     old = be.TC_MIN_MNK
+    old_bwd = ops.FUSE_RELU_BWD
     be.TC_MIN_MNK = 1 << 22
+    ops.FUSE_RELU_BWD = fuse_bwd   # also fold the ReLU-backward mask into the dX launch
     try:
         outs = []
         for fused in (True, False):
@@ -257,6 +261,7 @@ def test_dense_relu_fusion_is_transparent(size):
             assert np.array_equal(ga, gb)
     finally:
         be.TC_MIN_MNK = old
+        ops.FUSE_RELU_BWD = old_bwd
 
 
 def test_generic_step_path_equals_fused():

@@ -265,7 +265,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const float* __restrict__ bias, int flags, int t_full, int tail_split,
                    unsigned int* __restrict__ tile_flags, int group_m,
                    float* __restrict__ act_out, float* __restrict__ act_hi,
-                   float* __restrict__ act_lo, int64_t ld_act) {
+                   float* __restrict__ act_lo, int64_t ld_act,
+                   const float* __restrict__ mask_src) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -517,7 +518,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         float4* patch = reinterpret_cast<float4*>(smem_gen + C::STAGES * C::STAGE_BYTES + 256) +
                         (warp - 4) * 256;                       // 32 rows x 8 float4
         const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
-        const bool act_aligned = !emit_act || ((reinterpret_cast<uintptr_t>(act_out) & 15) == 0);
+        const bool act_aligned = !emit_act || (((reinterpret_cast<uintptr_t>(act_out) |
+                                                  reinterpret_cast<uintptr_t>(mask_src)) & 15) == 0);
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           const int colb = col0 + cb * 32;                      // first column of this 32-wide block
@@ -541,6 +543,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             patch[lane * 8 + (c4 ^ (lane & 7))] = v;
           }
           __syncwarp();
+          // whatever the store has to READ first (the previous D for accumulate, the pre-activation
+          // for the ReLU mask) is fetched for all 8 row groups up front: 8-16 independent 128-bit
+          // loads in flight instead of one exposed round trip per row group
+          // (one register array serves either purpose; a launch that wants both -- never issued by
+          // the engine -- reads the mask inside the loop)
+          const bool fast_rows = rows_aligned && act_aligned;
+          const bool want_mask = emit_act && mask_src != nullptr;
+          const float* pre_src = accumulate ? D : (want_mask ? mask_src : nullptr);
+          float4 pre[8];
+          if (fast_rows && pre_src != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int grow = row_base + 4 * i + (lane >> 3), gcol = colb + (lane & 7) * 4;
+              if (grow < M && gcol + 3 < N)
+                pre[i] = *reinterpret_cast<const float4*>(pre_src + (int64_t)grow * ldd + gcol);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + (lane >> 3), c4 = lane & 7;
@@ -548,9 +567,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const int grow = row_base + r, gcol = colb + c4 * 4;
             if (grow < M && gcol < N) {
               float* dp = D + (int64_t)grow * ldd + gcol;
-              if (gcol + 3 < N && rows_aligned && act_aligned) {
+              if (gcol + 3 < N && fast_rows) {
                 if (accumulate) {
-                  const float4 o = *reinterpret_cast<const float4*>(dp);
+                  const float4 o = pre[i];
                   v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
                 }
                 if (relu) {
@@ -561,8 +580,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 if (emit_act) {
                   // ReLU(D) (NaN-propagating like np.clip) and, optionally, its tf32 planes: the
                   // next product consumes the activation without a separate relu / split pass
-                  const float4 a = make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y,
-                                               v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+                  float4 a;
+                  if (mask_src) {
+                    // backward form: act = D * (pre-activation >= 0), the ReLU gradient mask of
+                    // ops.py:336-343 (grad * mask, so a masked NaN/inf stays NaN like numpy's)
+                    const float4 z = accumulate
+                        ? *reinterpret_cast<const float4*>(mask_src + (int64_t)grow * ldd + gcol)
+                        : pre[i];
+                    a = make_float4(z.x >= 0.f ? v.x : v.x * 0.f, z.y >= 0.f ? v.y : v.y * 0.f,
+                                    z.z >= 0.f ? v.z : v.z * 0.f, z.w >= 0.f ? v.w : v.w * 0.f);
+                  } else {
+                    a = make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y,
+                                    v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+                  }
                   *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = a;
                   if (act_hi) {
                     const float4 h = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
@@ -582,7 +612,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     if (relu) x = fmaxf(x, 0.f);
                     dp[k] = x;
                     if (emit_act) {
-                      const float a = x < 0.f ? 0.f : x;
+                      float a;
+                      if (mask_src) a = mask_src[(int64_t)grow * ldd + gcol + k] >= 0.f ? x : x * 0.f;
+                      else a = x < 0.f ? 0.f : x;
                       act_out[(int64_t)grow * ldd + gcol + k] = a;
                       if (act_hi) {
                         const float h = to_tf32(a);
@@ -732,6 +764,7 @@ struct ActOut {
   float* hi = nullptr;    // tf32 planes of relu(D), pitch ld
   float* lo = nullptr;
   int64_t ld = 0;
+  const float* mask_src = nullptr;   // when set: out = D * (mask_src >= 0) instead of relu(D)
 };
 
 template <int CG, bool A_MN, bool B_MN>
@@ -797,7 +830,7 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   cfg.numAttrs = 1;
   prof_begin(1);
   TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m,
-                              act.out, act.hi, act.lo, act.ld));
+                              act.out, act.hi, act.lo, act.ld, act.mask_src));
   ctx().launches++;
   prof_end(1);
   return 0;
@@ -862,7 +895,7 @@ int tnn_set_gemm_cta_group(int cg) {
 int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
                     const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
                     int64_t K, const float* bias, int flags, int layout, float* act_out,
-                    float* act_hi, float* act_lo, int64_t ld_act) {
+                    float* act_hi, float* act_lo, int64_t ld_act, const float* mask_src) {
   TNN_REQUIRE_INIT();
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) TNN_FAIL("tnn_gemm_tf32x3: K must be positive");
@@ -881,6 +914,7 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
     if ((act_hi == nullptr) != (act_lo == nullptr)) TNN_FAIL("tnn_gemm_tf32x3: act_hi/act_lo come in pairs");
     if (act_hi && (ld_act % 4 != 0 || ld_act < N)) TNN_FAIL("tnn_gemm_tf32x3: ld_act must be >= N and a multiple of 4");
     if (flags & 2) TNN_FAIL("tnn_gemm_tf32x3: act_out and the relu-in-place flag are exclusive");
+    act.mask_src = mask_src;
     act.out = act_out;
     act.hi = act_hi;
     act.lo = act_lo;
