@@ -73,7 +73,11 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: brackets the timed region inside a longer-running sampler"""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -83,7 +87,8 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = self.lines[first:last] or self.lines[-3:]
+        for ln in window:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -241,12 +246,13 @@ def run_b200_arm(args, cfg):
         return loss
 
     # ---- device-resident throughput ("value") --------------------------------------------------
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()                       # nvidia-smi needs ~0.3 s to produce its first sample
     for i in range(args.warmup):
         loss = train_step(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
     float(loss.values)
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    sampler.start()
     dist.barrier()
+    s_first = sampler.mark()
     be.prof_enable(1)
     launches0 = be.launch_count()
     ev0, ev1 = be.Event(), be.Event()
@@ -256,10 +262,11 @@ def run_b200_arm(args, cfg):
     ev1.record()
     dist.barrier()
     ms = ev1.elapsed_ms_since(ev0)
+    s_last = sampler.mark() + 1
     launches = be.launch_count() - launches0
     gemm_ms, gemm_n = be.prof_collect()
     be.prof_enable(0)
-    clocks = sampler.stop()
+    clocks = sampler.stop(s_first, s_last)
     last_loss = float(loss.values)
 
     # ---- end to end from host buffers ("e2e"): the public input pipeline ----------------------
