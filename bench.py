@@ -219,6 +219,11 @@ def run_b200_arm(args, cfg):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torchrun)" % (args.gpus, world))
     B = args.batch_per_gpu or cfg["batch"]
+    if args.global_batch:
+        lo, hi = dist.shard_bounds(args.global_batch, rank, world)
+        if (hi - lo) * world != args.global_batch:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        B = hi - lo
     C = cfg["widths"][-1]
     peaks = read_peaks()
 
@@ -344,7 +349,8 @@ def run_b200_arm(args, cfg):
         line = {
             "metric": "MLP train samples/sec", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)",
             "data": "synthetic",
             "config": make_config(cfg, B, world),
@@ -367,6 +373,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wide", choices=["wide", "mnist"])
     ap.add_argument("--batch-per-gpu", type=int, default=0)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fix the global batch (BASELINE config 5 uses 65536) and "
+                         "split it over the ranks; reported with \"scaling\": \"strong\"")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
