@@ -29,6 +29,7 @@ for s in $STAGES; do
     ab_fuse) for i in 1 2 3; do TNN_FUSE_RELU=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse1.log 2>&1; TNN_FUSE_RELU=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse0.log 2>&1; done ;;
     ncu_mnist) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv --log-file gpurun_out/launches_mnist.csv python bench.py --workload mnist --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/ncu_mnist.log 2>&1 ;;
     ab_bwd) for i in 1 2 3; do TNN_FUSE_RELU_BWD=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd1.log 2>&1; TNN_FUSE_RELU_BWD=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd0.log 2>&1; done ;;
+    ncu_mem) timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:adam_vec|relu_kernel|split_tf32|reduce_col|ce_bwd|ce_rows|ce_partial' -s 30 -c 18 -f -o gpurun_out/prof_mem python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mem.log 2>&1 ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt

@@ -27,7 +27,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "launch__grid_size", "launch__block_size", "launch__cluster_size",
            "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "sm__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
-           "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"]
+           "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+           "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+           "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 lst = os.path.join(G, "launches.csv")
 if os.path.exists(lst):
