@@ -242,7 +242,11 @@ def run_b200_arm(args, cfg):
     x_dev = [be.from_numpy(x_host.array[k]) for k in range(2)]
     y_dev = [be.from_numpy(y_host.array[k]) for k in range(2)]
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and args.workload == "mnist")
+
     def train_step(x_t, y_t):
+        if use_graph:   # the same five calls, recorded once per batch shape and replayed
+            return model.train_step(x_t, y_t)
         model.zero_grad()
         pred = model.forward(x_t)
         loss = loss_layer.loss(pred, y_t)
@@ -258,7 +262,8 @@ def run_b200_arm(args, cfg):
     float(loss.values)
     dist.barrier()
     s_first = sampler.mark()
-    be.prof_enable(1)
+    if not use_graph:
+        be.prof_enable(1)     # per-launch events around the tcgen05 GEMM (not recordable in a graph)
     launches0 = be.launch_count()
     ev0, ev1 = be.Event(), be.Event()
     ev0.record()
@@ -353,7 +358,8 @@ def run_b200_arm(args, cfg):
             "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)",
             "data": "synthetic",
-            "config": make_config(cfg, B, world),
+            "config": dict(make_config(cfg, B, world),
+                           step_mode="cuda_graph_replay" if use_graph else "eager_launches"),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(B * (cfg["d_in"] + C) * 4), "d2h_bytes_per_step": 4,
@@ -376,6 +382,9 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: fix the global batch (BASELINE config 5 uses 65536) and "
                          "split it over the ranks; reported with \"scaling\": \"strong\"")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as a CUDA graph (Model.train_step); auto = on for the "
+                         "launch-bound mnist workload, off for the wide MLP")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -72,6 +72,12 @@ _SIGNATURES = {
     "tnn_prof_enable": [_c_int],
     "tnn_prof_collect": [_c_vp, _c_vp],
     "tnn_l2_flush": [],
+    "tnn_graph_begin": [],
+    "tnn_graph_end": [_c_vp],
+    "tnn_graph_abort": [],
+    "tnn_graph_launch": [_c_vp],
+    "tnn_graph_info": [_c_vp, _c_vp, _c_vp, _c_vp],
+    "tnn_graph_destroy": [_c_vp],
     "tnn_ew": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                _c_dbl, _c_dbl, _c_int],
     "tnn_ew_flat": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_dbl, _c_dbl,
@@ -90,6 +96,10 @@ _SIGNATURES = {
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                         _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    "tnn_split_tf32_bf16": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64],
+    "tnn_gemm_tf32_bf16x2": [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64,
+                             _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
+                             _c_i64, _c_vp],
     "tnn_set_gemm_cta_group": [_c_int],
     "tnn_set_gemm_ksplit": [_c_int],
     "tnn_set_gemm_group_m": [_c_int],
@@ -101,6 +111,7 @@ _SIGNATURES = {
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
+    "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "tnn_nccl_unique_id": [_c_vp],
     "tnn_nccl_init": [_c_int, _c_int, _c_vp],
     "tnn_nccl_destroy": [],
@@ -289,6 +300,14 @@ def from_numpy(arr, dtype=None):
         if _lib.tnn_h2d(out.ptr, host.ctypes.data, host.nbytes):
             _raise("tnn_h2d")
     return out
+
+
+def upload_into(dst, host):
+    """host array -> existing device array (same dtype and element count)"""
+    host = np.require(host, dtype=dst.dtype, requirements="C")
+    assert host.size == dst.size
+    if host.size and _lib.tnn_h2d(dst.ptr, host.ctypes.data, host.nbytes):
+        _raise("tnn_h2d")
 
 
 def to_numpy(d):
@@ -578,6 +597,10 @@ def scatter_flat(g, idx_dev, shape):
 TC_MIN_MNK = int(os.environ.get("TNN_TC_MIN_MNK", str(1 << 26)))
 TC_ENABLED = os.environ.get("TNN_TC", "1") != "0"
 TC_MN_MAJOR = os.environ.get("TNN_TC_MN_MAJOR", "1") != "0"   # 0: transposed tf32 planes instead
+# operand split of the tensor-core product: "mix" = tf32 main term + bf16 cross terms (default),
+# "tf32x3" = three tf32 MMAs per K step (the textbook 3xTF32, kept as cross-check)
+TC_SPLIT = os.environ.get("TNN_GEMM_SPLIT", "mix")
+BF16_BYTES = 2
 _split_epoch = 0
 
 
@@ -589,6 +612,32 @@ def new_split_epoch():
 
 def _round4(n):
     return (n + 3) // 4 * 4
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+def _empty_bf16(rows, ld):
+    """raw bf16 plane (kept as a float32 DArray of half the width for bookkeeping)"""
+    return empty((rows, ld // 2), F32)
+
+
+def split_planes_mix(x):
+    """fp32 (R, C) -> (hi tf32 plane, bf16(x), bf16(x - hi), ld), cached for the step"""
+    cache = x.split
+    if cache is None or cache.get("epoch") != _split_epoch:
+        cache = {"epoch": _split_epoch}
+        x.split = cache
+    if "m" in cache:
+        return cache["m"]
+    R, C = x.shape
+    ld = _round8(C)
+    hi, h16, l16 = empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld)
+    if _lib.tnn_split_tf32_bf16(x.ptr, R, C, hi.ptr, h16.ptr, l16.ptr, ld):
+        _raise("tnn_split_tf32_bf16")
+    cache["m"] = (hi, h16, l16, ld)
+    return cache["m"]
 
 
 def split_planes(x, transposed, also_other=False):
@@ -674,6 +723,26 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
     if M == 0 or N == 0:
         return (out, act_out) if act else out
     flags = (1 if accumulate else 0) | (2 if relu else 0)
+    if K > 0 and use_tensor_cores(M, N, K, dt) and TC_SPLIT == "mix":
+        a_hi, a_h16, a_l16, lda = split_planes_mix(a)
+        b_hi, b_h16, b_l16, ldb = split_planes_mix(b)
+        layout = (1 if ta else 0) | (0 if tb else 2)
+        act_hi = act_h16 = act_l16 = None
+        ld_act = _round8(N)
+        if act:
+            act_hi = empty((M, ld_act), F32)
+            act_h16, act_l16 = _empty_bf16(M, ld_act), _empty_bf16(M, ld_act)
+        if _lib.tnn_gemm_tf32_bf16x2(out.ptr, N, a_hi.ptr, a_h16.ptr, a_l16.ptr, lda, b_hi.ptr,
+                                     b_h16.ptr, b_l16.ptr, ldb, M, N, K,
+                                     bias.ptr if bias is not None else None, flags, layout,
+                                     act_out.ptr if act else None, act_hi.ptr if act else None,
+                                     act_h16.ptr if act else None, act_l16.ptr if act else None,
+                                     ld_act, mask_src.ptr if (act and mask_src is not None) else None):
+            _raise("tnn_gemm_tf32_bf16x2")
+        if act:
+            act_out.split = {"epoch": _split_epoch, "m": (act_hi, act_h16, act_l16, ld_act)}
+            return out, act_out
+        return out
     if K > 0 and use_tensor_cores(M, N, K, dt):
         if TC_MN_MAJOR:
             # un-transposed planes only: a transposed operand is fed MN-major to the tensor core
@@ -771,6 +840,13 @@ def ce_bwd(z, y, stats, q, m_global, g):
 
 def opt_step(opt, param, step_out, grad, s0, s1, hyper):
     n = grad.size
+    if isinstance(hyper, DArray):    # captured step: coefficients live in device memory
+        if _lib.tnn_opt_step_dev(opt, _DT_CODE[grad.dtype], param.ptr if param is not None else None,
+                                 step_out.ptr if step_out is not None else None, grad.ptr,
+                                 s0.ptr if s0 is not None else None,
+                                 s1.ptr if s1 is not None else None, n, hyper.ptr):
+            _raise("tnn_opt_step_dev")
+        return
     h = (_c_dbl * len(hyper))(*hyper)
     if _lib.tnn_opt_step(opt, _DT_CODE[grad.dtype], param.ptr if param is not None else None,
                          step_out.ptr if step_out is not None else None, grad.ptr,
@@ -878,6 +954,67 @@ class Event(object):
                 _lib.tnn_event_destroy(self.ptr)
         except Exception:
             pass
+
+
+class StepGraph(object):
+    """A recorded sequence of device work (CUDA graph) that replay() re-issues with one call.
+
+        g = StepGraph()
+        with g.capture():
+            ... any device ops: they are recorded, not executed ...
+        g.replay()
+
+    Blocks allocated inside capture() belong to the graph until it is destroyed."""
+
+    def __init__(self):
+        init()
+        self.handle = None
+
+    def capture(self):
+        return _Capture(self)
+
+    def replay(self):
+        if _lib.tnn_graph_launch(self.handle):
+            _raise("tnn_graph_launch")
+
+    def info(self):
+        a, b, c = _c_sz(), _c_sz(), _c_sz()
+        if _lib.tnn_graph_info(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)):
+            _raise("tnn_graph_info")
+        return {"nodes": a.value, "kernel_nodes": b.value, "blocks": c.value}
+
+    def destroy(self):
+        if self.handle and _lib is not None:
+            _lib.tnn_graph_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class _Capture(object):
+    def __init__(self, graph):
+        self.graph = graph
+
+    def __enter__(self):
+        if self.graph.handle:
+            raise BackendError("StepGraph already holds a captured step")
+        if _lib.tnn_graph_begin():
+            _raise("tnn_graph_begin")
+        return self.graph
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None:
+            _lib.tnn_graph_abort()
+            return False
+        h = _c_vp()
+        if _lib.tnn_graph_end(ctypes.byref(h)):
+            _raise("tnn_graph_end")
+        self.graph.handle = h.value
+        return False
 
 
 def prof_enable(family):

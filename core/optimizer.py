@@ -31,6 +31,7 @@ class BaseOptimizer(object):
         self.lr = lr
         self.weight_decay = weight_decay
         self._state = None  # list of flat device vectors, allocated at the first step
+        self._hyper_dev = None  # device copy of the hyper-parameters while a captured step uses them
 
     # ---- reference interface ------------------------------------------------------------
     def compute_step(self, grads, params):
@@ -79,7 +80,16 @@ class BaseOptimizer(object):
             raise ValueError("optimizer state was built for %d parameters of %s, got %d of %s"
                              % (self._state[0].size, self._state[0].dtype, grad.size, grad.dtype))
         s = self._state + [None, None]
-        be.opt_step(self.opt_code, param, step_out, grad, s[0], s[1], self._hyper())
+        hyper = self._hyper_dev if self._hyper_dev is not None else self._hyper()
+        be.opt_step(self.opt_code, param, step_out, grad, s[0], s[1], hyper)
+
+    def upload_hyper(self, dst):
+        """advance to the next step (Adam: t += 1) and put its coefficients into the 8-double device
+        vector a captured step reads them from"""
+        h = np.zeros(8, dtype=np.float64)
+        vals = self._hyper()
+        h[:len(vals)] = vals
+        be.upload_into(dst, h)
 
     def _hyper(self):
         raise NotImplementedError

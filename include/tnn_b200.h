@@ -117,6 +117,21 @@ int tnn_prof_enable(int family);          /* 0 = off, 1 = tcgen05 GEMM, 2 = SIMT
 int tnn_prof_collect(double* total_ms, uint64_t* n_launches); /* synchronises, then resets */
 int tnn_l2_flush(void);                   /* writes a buffer larger than L2 */
 
+/* ---- captured steps (CUDA graphs) -----------------------------------------------------------
+ * One training step of examples/mnist/run.py:78-83 (zero_grad, forward, loss, backward, step) is
+ * ~35 launches of a few microseconds each; issued one at a time from Python it is launch-bound.
+ * Everything queued on the compute stream between tnn_graph_begin and tnn_graph_end (kernels,
+ * memsets, device copies, NCCL collectives) is recorded instead of executed; tnn_graph_launch
+ * replays it with one call.  Blocks handed out by tnn_alloc during the capture belong to the
+ * graph (addresses are baked into its nodes): they are reused inside the capture but only return
+ * to the pool at tnn_graph_destroy.  tnn_h2d / tnn_d2h fail during a capture. */
+int tnn_graph_begin(void);
+int tnn_graph_end(void** graph_out);
+int tnn_graph_abort(void);                /* drop a capture in progress (host-side error path) */
+int tnn_graph_launch(void* graph);        /* one replay on the compute stream */
+int tnn_graph_info(void* graph, size_t* n_nodes, size_t* n_kernel_nodes, size_t* n_blocks);
+int tnn_graph_destroy(void* graph);
+
 /* ---- elementwise with numpy broadcasting (core/ops.py:32-249, 293-299, 333-344) ------------ */
 /* out is contiguous with shape[ndim]; xs/ys/zs are element strides (0 = broadcast); y, z may be
  * NULL for unary/binary ops. p0/p1/flags are op parameters (clip bounds, scale). */
@@ -182,6 +197,23 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd,
                     int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout,
                     float* act_out, float* act_hi, float* act_lo, int64_t ld_act,
                     const float* mask_src);
+/* Mixed split (default path): the two cross terms of the 3xTF32 expansion need only ~9 significant
+ * bits per factor, so they run as BF16 MMAs at twice the TF32 rate:
+ *     A*B ~= bf16(A - A_hi)*bf16(B) + bf16(A)*bf16(B - B_hi) + A_hi*B_hi,   A_hi = tf32(A)
+ * 8 tensor-pipe slots per 32-wide K block instead of 12, same 8 B/element of planes.  Split error
+ * 7e-7 of max|A@B| (3xTF32: 7e-8), below the fp32 accumulation error of the K loop.
+ * tnn_split_tf32_bf16: x [R, C] -> hi (fp32 plane, tf32 values), h16 = bf16(x), l16 = bf16(x - hi),
+ *   all with pitch ld elements (multiple of 8, >= C; pad columns are zeroed).
+ * tnn_gemm_tf32_bf16x2: same contract as tnn_gemm_tf32x3 (layout bits, flags, fused activation
+ *   outputs, mask_src), operands and the activation planes in the three-plane form. */
+int tnn_split_tf32_bf16(const float* x, int64_t R, int64_t C, float* hi, void* h16, void* l16,
+                        int64_t ld);
+int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
+                         const float* a_hi, const void* a_h16, const void* a_l16, int64_t lda,
+                         const float* b_hi, const void* b_h16, const void* b_l16, int64_t ldb,
+                         int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout,
+                         float* act_out, float* act_hi, void* act_h16, void* act_l16, int64_t ld_act,
+                         const float* mask_src);
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);
@@ -222,6 +254,10 @@ int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, i
  * param (updated in place: param += step) and step_out (receives step) may each be NULL. */
 int tnn_opt_step(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
                  void* s1, int64_t n, const double* h, int n_h);
+/* same, with the 8 hyper-parameter doubles read from DEVICE memory at run time: the form a
+ * captured step uses, because Adam's 1-b^t terms (optimizer.py:74-75) change at every replay */
+int tnn_opt_step_dev(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
+                     void* s1, int64_t n, const double* h_dev);
 
 /* ---- data-parallel collectives (new: the reference has none) -------------------- */
 int tnn_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId */

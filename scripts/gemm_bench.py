@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--cg", default="1,2")
     ap.add_argument("--ksplit", default="0,1")
     ap.add_argument("--group-m", default="1,-8,-4,1,-8,-4")
+    ap.add_argument("--sustain", type=int, default=0,
+                    help="also time this many back-to-back launches (power-capped steady state)")
     args = ap.parse_args()
     be.init()
     B, D = args.batch, args.width
@@ -57,8 +59,16 @@ def main():
                 fn(outs[name])
                 e1.record()
                 best = min(best, e1.elapsed_ms_since(e0))
-            print(json.dumps(dict(shape=name, cg=cg, ksplit=ks, group_m=gm, ms=round(best, 4),
-                                  tflops=round(flops / best / 1e9, 1))))
+            rec = dict(shape=name, cg=cg, ksplit=ks, group_m=gm, ms=round(best, 4),
+                       tflops=round(flops / best / 1e9, 1))
+            if args.sustain:
+                e0.record()
+                for _ in range(args.sustain):
+                    fn(outs[name])
+                e1.record()
+                sus = e1.elapsed_ms_since(e0) / args.sustain
+                rec.update(sustained_ms=round(sus, 4), sustained_tflops=round(flops / sus / 1e9, 1))
+            print(json.dumps(rec))
 
 
 if __name__ == "__main__":

@@ -30,11 +30,15 @@ for s in $STAGES; do
     ncu_mnist) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv --log-file gpurun_out/launches_mnist.csv python bench.py --workload mnist --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/ncu_mnist.log 2>&1 ;;
     ab_bwd) for i in 1 2 3; do TNN_FUSE_RELU_BWD=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd1.log 2>&1; TNN_FUSE_RELU_BWD=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_bwd0.log 2>&1; done ;;
     ncu_mem) timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:adam_vec|relu_kernel|split_tf32|reduce_col|ce_bwd|ce_rows|ce_partial' -s 30 -c 18 -f -o gpurun_out/prof_mem python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mem.log 2>&1 ;;
+    gemmbench2) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1 --sustain 500 > gpurun_out/gemm_bench_mix.jsonl 2>&1; TNN_GEMM_SPLIT=tf32x3 timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1 --sustain 500 > gpurun_out/gemm_bench_tf32x3.jsonl 2>&1 ;;
+    graph) timeout 900 python -m pytest tests/test_gpu_graph.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_graph.log 2>&1 ;;
+    mnist_ab) for g in on off on off; do timeout 300 python bench.py --workload mnist --steps 2000 --warmup 50 --graph $g --no-cpu-baseline >> gpurun_out/bench_mnist_graph_$g.log 2>&1; done ;;
+    ncu_mnist_graph) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -s 400 -c 200 --csv --log-file gpurun_out/launches_mnist_graph.csv python bench.py --workload mnist --steps 20 --warmup 10 --graph on --no-cpu-baseline > gpurun_out/ncu_mnist_graph.log 2>&1 ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt
 done
-for f in gpurun_out/smoke.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/memcheck.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
+for f in gpurun_out/smoke.log gpurun_out/gemm_bench_mix.jsonl gpurun_out/gemm_bench_tf32x3.jsonl gpurun_out/pytest_graph.log gpurun_out/pytest_all.log gpurun_out/bench_mnist_graph_on.log gpurun_out/bench_mnist_graph_off.log gpurun_out/ncu_mnist_graph.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/memcheck.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
   [ -f $f ] && { echo "== $f"; tail -n 6 $f; }
 done
 cat gpurun_out/stages.txt

@@ -42,19 +42,46 @@ def test_split_planes_reconstruct(be):
         assert np.array_equal(HT, H.T) and np.array_equal(LT, L.T)
 
 
-@pytest.mark.parametrize("mn_major", [True, False])
+def _bf16_rn(x):
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x7FFF + ((b >> 16) & 1)) >> 16
+    return b.astype(np.uint16)
+
+
+def test_mixed_split_planes(be):
+    """hi = tf32(x) in an fp32 plane, h16 = bf16(x), l16 = bf16(x - hi); pad columns are zero"""
+    rng = np.random.RandomState(0)
+    for R_, C_ in ((64, 64), (130, 70), (257, 33), (5, 1000), (3, 1)):
+        x = (rng.standard_normal((R_, C_)) * 10 ** rng.uniform(-3, 3, (R_, C_))).astype(np.float32)
+        d = be.from_numpy(x)
+        hi, h16, l16, ld = be.split_planes_mix(d)
+        assert ld % 8 == 0 and ld >= C_
+        H = hi.numpy()
+        H16 = h16.numpy().view(np.uint16).reshape(R_, ld)
+        L16 = l16.numpy().view(np.uint16).reshape(R_, ld)
+        assert np.all(H[:, C_:] == 0) and np.all(H16[:, C_:] == 0) and np.all(L16[:, C_:] == 0)
+        H = H[:, :C_]
+        assert np.all(H.view(np.uint32) & 0x1FFF == 0)
+        assert np.max(np.abs(H.astype(np.float64) - x) / np.abs(x)) <= 2.0 ** -11
+        assert np.array_equal(H16[:, :C_], _bf16_rn(x))
+        assert np.array_equal(L16[:, :C_], _bf16_rn(x - H))
+
+
+@pytest.mark.parametrize("split,mn_major", [("mix", True), ("tf32x3", True), ("tf32x3", False)])
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("shape", [
     (128, 256, 32), (128, 256, 64), (256, 256, 128), (256, 512, 96), (384, 768, 200),
     (100, 300, 52), (129, 257, 36), (1000, 520, 260), (2048, 1024, 512),
 ])
-def test_tf32x3_gemm_shapes(be, cg, shape, mn_major):
-    """NN / NT / TN products; mn_major=True feeds transposed operands MN-major from the plain tf32
+def test_tf32x3_gemm_shapes(be, cg, shape, split, mn_major):
+    """NN / NT / TN products.  split = "mix": tf32 main term + bf16 cross terms (the default path);
+    "tf32x3": three tf32 MMAs.  mn_major=True feeds transposed operands MN-major from the plain
     planes (default), False goes through transposed planes (both operands K-major)"""
     M, N, K = shape
     be.set_gemm_cta_group(cg)
-    old_mn = be.TC_MN_MAJOR
+    old_mn, old_split = be.TC_MN_MAJOR, be.TC_SPLIT
     be.TC_MN_MAJOR = mn_major
+    be.TC_SPLIT = split
     try:
         rng = np.random.RandomState(M * 7 + N * 3 + K)
         a = rng.standard_normal((M, K)).astype(np.float32)
@@ -84,7 +111,47 @@ def test_tf32x3_gemm_shapes(be, cg, shape, mn_major):
             be.TC_MIN_MNK = old
     finally:
         be.TC_MN_MAJOR = old_mn
+        be.TC_SPLIT = old_split
         be.set_gemm_cta_group(0)
+
+
+@pytest.mark.parametrize("split", ["mix", "tf32x3"])
+def test_fused_activation_outputs(be, split):
+    """act=True: one launch returns the pre-activation, its ReLU and the ReLU's operand planes,
+    which the next product consumes as-is; mask_src form returns out * (mask_src >= 0)"""
+    rng = np.random.RandomState(5)
+    M, N, K = 300, 264, 136
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal((1, N)).astype(np.float32)
+    w2 = rng.standard_normal((N, 72)).astype(np.float32)
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK = 0
+    be.TC_SPLIT = split
+    try:
+        z, act = be.matmul(be.from_numpy(a), be.from_numpy(b), bias=be.from_numpy(bias), act=True)
+        zr = _ref(a, b, False, False, bias)
+        assert op_cases.rel_err(z.numpy(), zr) <= TOL
+        assert np.array_equal(act.numpy(), np.maximum(z.numpy(), 0))
+        # the planes attached to `act` must equal a fresh split of it
+        key = "m" if split == "mix" else "p"
+        fused = [p.numpy() for p in act.split[key][:-1]]
+        act.split = None
+        fresh_planes = be.split_planes_mix(act) if split == "mix" else be.split_planes(act, transposed=False)
+        N_ = act.shape[1]
+        for f, g in zip(fused, [p.numpy() for p in fresh_planes[:-1]]):
+            w = N_ if f.shape[1] >= N_ else N_ // 2       # bf16 planes are kept as half-width fp32
+            assert np.array_equal(f[:, :w], g[:, :w])
+        # and the next product consumes them
+        act2 = be.from_numpy(np.maximum(z.numpy(), 0))
+        y_fused = be.matmul(act, be.from_numpy(w2)).numpy()
+        y_plain = be.matmul(act2, be.from_numpy(w2)).numpy()
+        assert np.array_equal(y_fused, y_plain)
+        pre = rng.standard_normal((M, N)).astype(np.float32)
+        g, masked = be.matmul(be.from_numpy(a), be.from_numpy(b), act=True, mask_src=be.from_numpy(pre))
+        assert np.array_equal(masked.numpy(), g.numpy() * (pre >= 0))
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
 
 
 @pytest.mark.parametrize("cg", [1, 2])

@@ -300,7 +300,9 @@ struct OptH {
 
 template <int OPT, typename T>
 __global__ void __launch_bounds__(256)
-opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH hh) {
+opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH hh,
+           const OptH* hdev) {
+  if (hdev) hh = *hdev;   // captured step: the coefficients are refreshed in device memory per replay
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const T g = grad[i];
@@ -355,7 +357,8 @@ opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH h
 // Adam is the hot one (28 B/param): 128-bit variant
 template <typename T>
 __global__ void __launch_bounds__(256)
-adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh) {
+adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh, const OptH* hdev) {
+  if (hdev) hh = *hdev;
   using VT = typename V4<T>::type;
   using U = typename V4<T>::U;
   constexpr int W = V4<T>::W;
@@ -383,41 +386,41 @@ adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh) {
 
 template <typename T>
 static int opt_dispatch(int opt, T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n,
-                        const OptH& hh) {
+                        const OptH& hh, const OptH* hdev) {
   cudaStream_t st = ctx().stream;
   int grid = ew_grid(n, 256);
   switch (opt) {
     case TNN_OPT_SGD:
-      opt_kernel<TNN_OPT_SGD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      opt_kernel<TNN_OPT_SGD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       break;
     case TNN_OPT_ADAM: {
       constexpr int W = V4<T>::W;
       if (param && !step_out && al16(param) && al16(grad) && al16(s0) && al16(s1) && n >= W) {
         int64_t nv = n / W;
-        adam_vec_kernel<T><<<ew_grid(nv, 256), 256, 0, st>>>(param, grad, s0, s1, nv, hh);
+        adam_vec_kernel<T><<<ew_grid(nv, 256), 256, 0, st>>>(param, grad, s0, s1, nv, hh, hdev);
         TNN_POST_LAUNCH();
         int64_t done = nv * W;
         if (done < n)
           opt_kernel<TNN_OPT_ADAM, T><<<1, 256, 0, st>>>(param + done, nullptr, grad + done,
-                                                         s0 + done, s1 + done, n - done, hh);
+                                                         s0 + done, s1 + done, n - done, hh, hdev);
         else
           return 0;
       } else {
-        opt_kernel<TNN_OPT_ADAM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+        opt_kernel<TNN_OPT_ADAM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       }
       break;
     }
     case TNN_OPT_RMSPROP:
-      opt_kernel<TNN_OPT_RMSPROP, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      opt_kernel<TNN_OPT_RMSPROP, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       break;
     case TNN_OPT_MOMENTUM:
-      opt_kernel<TNN_OPT_MOMENTUM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      opt_kernel<TNN_OPT_MOMENTUM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       break;
     case TNN_OPT_ADAGRAD:
-      opt_kernel<TNN_OPT_ADAGRAD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      opt_kernel<TNN_OPT_ADAGRAD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       break;
     case TNN_OPT_ADADELTA:
-      opt_kernel<TNN_OPT_ADADELTA, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh);
+      opt_kernel<TNN_OPT_ADADELTA, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
       break;
     default:
       TNN_FAIL("tnn_opt_step: unknown optimizer code");
@@ -568,10 +571,24 @@ int tnn_opt_step(int opt, int dtype, void* param, void* step_out, const void* gr
   OptH hh;
   for (int i = 0; i < 8; ++i) hh.h[i] = i < n_h ? h[i] : 0.0;
   if (dtype == TNN_F32)
-    return opt_dispatch<float>(opt, (float*)param, (float*)step_out, (const float*)grad, (float*)s0, (float*)s1, n, hh);
+    return opt_dispatch<float>(opt, (float*)param, (float*)step_out, (const float*)grad, (float*)s0, (float*)s1, n, hh, nullptr);
   if (dtype == TNN_F64)
-    return opt_dispatch<double>(opt, (double*)param, (double*)step_out, (const double*)grad, (double*)s0, (double*)s1, n, hh);
+    return opt_dispatch<double>(opt, (double*)param, (double*)step_out, (const double*)grad, (double*)s0, (double*)s1, n, hh, nullptr);
   TNN_FAIL("tnn_opt_step: bad dtype");
+}
+
+int tnn_opt_step_dev(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
+                     void* s1, int64_t n, const double* h_dev) {
+  TNN_REQUIRE_INIT();
+  if (n <= 0) return 0;
+  if (!h_dev) TNN_FAIL("tnn_opt_step_dev: h_dev is NULL");
+  OptH hh = {};
+  const OptH* hd = reinterpret_cast<const OptH*>(h_dev);
+  if (dtype == TNN_F32)
+    return opt_dispatch<float>(opt, (float*)param, (float*)step_out, (const float*)grad, (float*)s0, (float*)s1, n, hh, hd);
+  if (dtype == TNN_F64)
+    return opt_dispatch<double>(opt, (double*)param, (double*)step_out, (const double*)grad, (double*)s0, (double*)s1, n, hh, hd);
+  TNN_FAIL("tnn_opt_step_dev: bad dtype");
 }
 
 }  // extern "C"

@@ -23,7 +23,19 @@
 //                            128 rows of A and half of B -> half the L2->SMEM operand traffic
 //                            per flop and room for a third pipeline stage.
 // Algorithmic work: 2*M*N*K flop per call; the tensor pipe executes 3x that in TF32.
+//
+// MIX variant (tnn_gemm_tf32_bf16x2, the default): the two cross terms only need ~9 significant
+// bits of each factor, so they run as BF16 MMAs (twice the TF32 rate) on bf16 planes:
+//
+//     A*B ~= bf16(A - A_hi)*bf16(B) + bf16(A)*bf16(B - B_hi) + A_hi*B_hi
+//
+// Per 32-wide K block that is 2+2 BF16 MMAs (K = 16) and 4 TF32 MMAs (K = 8): 8 tensor-pipe
+// slots instead of 12, with the same 8 bytes of planes per element (hi fp32 + two bf16 planes).
+// The split error grows from 7e-8 to 7e-7 of max|result| (numpy emulation in DESIGN.md) -- still
+// below the fp32 accumulation error of a K = 4096 product.  The kernel is power-bound (SM clocks
+// settle near 1.7 GHz under the 1 kW cap), so a third fewer MMA cycles is a fifth less time.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -167,6 +179,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // commit all prior MMAs of this thread to an mbarrier (implies fence::before_thread_sync)
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -219,10 +245,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)(MN ? 1 : 2) << 61;                         // SWIZZLE_128B_BASE32B : SWIZZLE_128B
   return d;
 }
+// bf16 planes (MIX variant), one 32-wide K block:
+//   K-major  : one TMA box {32 k, rows} of 64-byte rows, 64-byte swizzle (period 8 rows = 512 B).
+//              Descriptor: SWIZZLE_64B, 8-row groups 512 B apart (SBO); a K=16 step advances 32 B.
+//   MN-major : rows/64 TMA boxes {64 mn, 32 k} of 4096 B (k-row j at j*128 B holding 64 consecutive
+//              M/N elements), plain 128-byte swizzle.  Descriptor: SWIZZLE_128B, 8-k groups 1024 B
+//              apart (SBO), 64-element M/N chunks 4096 B apart (LBO); a K=16 step advances 2048 B.
+template <bool MN>
+__device__ __forceinline__ uint64_t make_smem_desc16(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(MN ? (4096 >> 4) : 1) << 16;
+  d |= (uint64_t)((MN ? 1024 : 512) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(MN ? 2 : 4) << 61;                         // SWIZZLE_128B : SWIZZLE_64B
+  return d;
+}
 constexpr int MN_BOX_BYTES = 32 * PLANE_ROW_BYTES;           // one {32 mn, 32 k} box
 // instruction descriptor: D=F32, A=B=TF32, operand majors, N, M
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// D=F32, A=B=BF16
+__host__ __device__ constexpr uint32_t make_idesc16(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -255,17 +303,21 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 }
 
 // ---- the GEMM kernel ---------------------------------------------------------------------------
-template <int CG, bool A_MN, bool B_MN>
+// MIX = false: planes are (hi, lo) tf32, map_*_lo = the lo plane, map_*_l16 unused.
+// MIX = true : planes are (hi tf32, h16 = bf16(x), l16 = bf16(x - hi)); map_*_lo = h16.
+template <int CG, bool A_MN, bool B_MN, bool MIX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_a_l16,
                    const __grid_constant__ CUtensorMap map_b_hi,
                    const __grid_constant__ CUtensorMap map_b_lo,
+                   const __grid_constant__ CUtensorMap map_b_l16,
                    float* __restrict__ D, int64_t ldd, int M, int N, int K,
                    const float* __restrict__ bias, int flags, int t_full, int tail_split,
                    unsigned int* __restrict__ tile_flags, int group_m,
                    float* __restrict__ act_out, float* __restrict__ act_hi,
-                   float* __restrict__ act_lo, int64_t ld_act,
+                   float* __restrict__ act_lo, __nv_bfloat16* __restrict__ act_l16, int64_t ld_act,
                    const float* __restrict__ mask_src) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
@@ -291,6 +343,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi);
     tma_prefetch_desc(&map_b_lo);
+    if constexpr (MIX) {
+      tma_prefetch_desc(&map_a_l16);
+      tma_prefetch_desc(&map_b_l16);
+    }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -363,25 +419,59 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t sb_lo = sb_hi + C::B_BYTES;
           if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)C::STAGE_BYTES * CG);
           const int k0 = kb * BK;
-          if constexpr (A_MN) {
+          if constexpr (!MIX) {
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int j = 0; j < ROWS_A / 32; ++j) {
-              tma_load_2d<CG>(sa_hi + j * MN_BOX_BYTES, &map_a_hi, full_bar(stage), row_a + 32 * j, k0);
-              tma_load_2d<CG>(sa_lo + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 32 * j, k0);
+              for (int j = 0; j < ROWS_A / 32; ++j) {
+                tma_load_2d<CG>(sa_hi + j * MN_BOX_BYTES, &map_a_hi, full_bar(stage), row_a + 32 * j, k0);
+                tma_load_2d<CG>(sa_lo + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 32 * j, k0);
+              }
+            } else {
+              tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
+              tma_load_2d<CG>(sa_lo, &map_a_lo, full_bar(stage), k0, row_a);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < C::ROWS_B / 32; ++j) {
+                tma_load_2d<CG>(sb_hi + j * MN_BOX_BYTES, &map_b_hi, full_bar(stage), row_b + 32 * j, k0);
+                tma_load_2d<CG>(sb_lo + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 32 * j, k0);
+              }
+            } else {
+              tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
+              tma_load_2d<CG>(sb_lo, &map_b_lo, full_bar(stage), k0, row_b);
             }
           } else {
-            tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
-            tma_load_2d<CG>(sa_lo, &map_a_lo, full_bar(stage), k0, row_a);
-          }
-          if constexpr (B_MN) {
+            // the second 32-bit plane's space holds the two bf16 planes
+            const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::A_BYTES / 2;
+            const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::B_BYTES / 2;
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int j = 0; j < C::ROWS_B / 32; ++j) {
-              tma_load_2d<CG>(sb_hi + j * MN_BOX_BYTES, &map_b_hi, full_bar(stage), row_b + 32 * j, k0);
-              tma_load_2d<CG>(sb_lo + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 32 * j, k0);
+              for (int j = 0; j < ROWS_A / 32; ++j)
+                tma_load_2d<CG>(sa_hi + j * MN_BOX_BYTES, &map_a_hi, full_bar(stage), row_a + 32 * j, k0);
+#pragma unroll
+              for (int j = 0; j < ROWS_A / 64; ++j) {
+                tma_load_2d<CG>(sa_h16 + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 64 * j, k0);
+                tma_load_2d<CG>(sa_l16 + j * MN_BOX_BYTES, &map_a_l16, full_bar(stage), row_a + 64 * j, k0);
+              }
+            } else {
+              tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
+              tma_load_2d<CG>(sa_h16, &map_a_lo, full_bar(stage), k0, row_a);
+              tma_load_2d<CG>(sa_l16, &map_a_l16, full_bar(stage), k0, row_a);
             }
-          } else {
-            tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
-            tma_load_2d<CG>(sb_lo, &map_b_lo, full_bar(stage), k0, row_b);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < C::ROWS_B / 32; ++j)
+                tma_load_2d<CG>(sb_hi + j * MN_BOX_BYTES, &map_b_hi, full_bar(stage), row_b + 32 * j, k0);
+#pragma unroll
+              for (int j = 0; j < C::ROWS_B / 64; ++j) {
+                tma_load_2d<CG>(sb_h16 + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 64 * j, k0);
+                tma_load_2d<CG>(sb_l16 + j * MN_BOX_BYTES, &map_b_l16, full_bar(stage), row_b + 64 * j, k0);
+              }
+            } else {
+              tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
+              tma_load_2d<CG>(sb_h16, &map_b_lo, full_bar(stage), k0, row_b);
+              tma_load_2d<CG>(sb_l16, &map_b_l16, full_bar(stage), k0, row_b);
+            }
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -395,6 +485,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(C::TILE_M, UMMA_N, A_MN, B_MN);
+      constexpr uint32_t idesc16 = make_idesc16(C::TILE_M, UMMA_N, A_MN, B_MN);
+      (void)idesc16;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -414,19 +506,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint32_t sa_lo = sa_hi + C::A_BYTES;
             const uint32_t sb_hi = sa_lo + C::A_BYTES;
             const uint32_t sb_lo = sb_hi + C::B_BYTES;
+            if constexpr (!MIX) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // a K=8 step: 32 B along the row (K-major) or one 8-row group of 1024 B (MN-major)
-              const uint32_t koff_a = (uint32_t)(k * (A_MN ? 1024 : UMMA_K * 4));
-              const uint32_t koff_b = (uint32_t)(k * (B_MN ? 1024 : UMMA_K * 4));
-              const uint64_t da_hi = make_smem_desc<A_MN>(sa_hi + koff_a);
-              const uint64_t da_lo = make_smem_desc<A_MN>(sa_lo + koff_a);
-              const uint64_t db_hi = make_smem_desc<B_MN>(sb_hi + koff_b);
-              const uint64_t db_lo = make_smem_desc<B_MN>(sb_lo + koff_b);
-              // small terms first; the first MMA of a chunk overwrites the accumulator
-              umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-              umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
-              umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // a K=8 step: 32 B along the row (K-major) or one 8-row group of 1024 B (MN-major)
+                const uint32_t koff_a = (uint32_t)(k * (A_MN ? 1024 : UMMA_K * 4));
+                const uint32_t koff_b = (uint32_t)(k * (B_MN ? 1024 : UMMA_K * 4));
+                const uint64_t da_hi = make_smem_desc<A_MN>(sa_hi + koff_a);
+                const uint64_t da_lo = make_smem_desc<A_MN>(sa_lo + koff_a);
+                const uint64_t db_hi = make_smem_desc<B_MN>(sb_hi + koff_b);
+                const uint64_t db_lo = make_smem_desc<B_MN>(sb_lo + koff_b);
+                // small terms first; the first MMA of a chunk overwrites the accumulator
+                umma_tf32<CG>(tmem_d, da_lo, db_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                umma_tf32<CG>(tmem_d, da_hi, db_lo, idesc, 1u);
+                umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
+              }
+            } else {
+              const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::A_BYTES / 2;
+              const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::B_BYTES / 2;
+              // cross terms on the bf16 planes (small terms first): two K=16 steps
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t koff_a = (uint32_t)(k * (A_MN ? 2048 : 32));
+                const uint32_t koff_b = (uint32_t)(k * (B_MN ? 2048 : 32));
+                const uint64_t da_h = make_smem_desc16<A_MN>(sa_h16 + koff_a);
+                const uint64_t da_l = make_smem_desc16<A_MN>(sa_l16 + koff_a);
+                const uint64_t db_h = make_smem_desc16<B_MN>(sb_h16 + koff_b);
+                const uint64_t db_l = make_smem_desc16<B_MN>(sb_l16 + koff_b);
+                umma_bf16<CG>(tmem_d, da_l, db_h, idesc16, (kb != kb0 || k != 0) ? 1u : 0u);
+                umma_bf16<CG>(tmem_d, da_h, db_l, idesc16, 1u);
+              }
+              // main term on the tf32 planes: four K=8 steps
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint32_t koff_a = (uint32_t)(k * (A_MN ? 1024 : UMMA_K * 4));
+                const uint32_t koff_b = (uint32_t)(k * (B_MN ? 1024 : UMMA_K * 4));
+                umma_tf32<CG>(tmem_d, make_smem_desc<A_MN>(sa_hi + koff_a),
+                              make_smem_desc<B_MN>(sb_hi + koff_b), idesc, 1u);
+              }
             }
             umma_commit<CG>(empty_bar(stage));          // frees the smem slot when the MMAs retire
             if (++stage == C::STAGES) {
@@ -596,10 +713,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                   *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = a;
                   if (act_hi) {
                     const float4 h = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
-                    const float4 l = make_float4(to_tf32(a.x - h.x), to_tf32(a.y - h.y),
-                                                 to_tf32(a.z - h.z), to_tf32(a.w - h.w));
                     *reinterpret_cast<float4*>(act_hi + (int64_t)grow * ld_act + gcol) = h;
-                    *reinterpret_cast<float4*>(act_lo + (int64_t)grow * ld_act + gcol) = l;
+                    if constexpr (!MIX) {
+                      const float4 l = make_float4(to_tf32(a.x - h.x), to_tf32(a.y - h.y),
+                                                   to_tf32(a.z - h.z), to_tf32(a.w - h.w));
+                      *reinterpret_cast<float4*>(act_lo + (int64_t)grow * ld_act + gcol) = l;
+                    } else {
+                      __nv_bfloat16* h16p = reinterpret_cast<__nv_bfloat16*>(act_lo);
+                      union { __nv_bfloat162 b[2]; uint2 u; } ph, pl;
+                      ph.b[0] = __floats2bfloat162_rn(a.x, a.y);
+                      ph.b[1] = __floats2bfloat162_rn(a.z, a.w);
+                      pl.b[0] = __floats2bfloat162_rn(a.x - h.x, a.y - h.y);
+                      pl.b[1] = __floats2bfloat162_rn(a.z - h.z, a.w - h.w);
+                      *reinterpret_cast<uint2*>(h16p + (int64_t)grow * ld_act + gcol) = ph.u;
+                      *reinterpret_cast<uint2*>(act_l16 + (int64_t)grow * ld_act + gcol) = pl.u;
+                    }
                   }
                 }
               } else {
@@ -619,7 +747,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                       if (act_hi) {
                         const float h = to_tf32(a);
                         act_hi[(int64_t)grow * ld_act + gcol + k] = h;
-                        act_lo[(int64_t)grow * ld_act + gcol + k] = to_tf32(a - h);
+                        if constexpr (!MIX) {
+                          act_lo[(int64_t)grow * ld_act + gcol + k] = to_tf32(a - h);
+                        } else {
+                          reinterpret_cast<__nv_bfloat16*>(act_lo)[(int64_t)grow * ld_act + gcol + k] =
+                              __float2bfloat16_rn(a);
+                          act_l16[(int64_t)grow * ld_act + gcol + k] = __float2bfloat16_rn(a - h);
+                        }
                       }
                     }
                   }
@@ -718,6 +852,45 @@ split_tf32_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __re
   }
 }
 
+// fp32 [R, C] -> hi = tf32(x) (fp32 plane), h16 = bf16(x), l16 = bf16(x - hi), all with pitch ld
+// (a multiple of 8 >= C; the pad columns receive zeros).  One thread per 8 consecutive columns:
+// two 128-bit loads, two 128-bit hi stores, one 128-bit store per bf16 plane.  12 B/element.
+__global__ void __launch_bounds__(256)
+split_mix_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __restrict__ hi,
+                 __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ l16, int64_t ld,
+                 int vec_in) {
+  const int64_t gpr = ld / 8;   // 8-column groups per row
+  const int64_t total = R * gpr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / gpr, c = (i - r * gpr) * 8;
+    float v[8];
+    if (vec_in && c + 7 < C) {
+      const float4 t0 = *reinterpret_cast<const float4*>(x + r * C + c);
+      const float4 t1 = *reinterpret_cast<const float4*>(x + r * C + c + 4);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+      v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (c + k < C) ? x[r * C + c + k] : 0.f;
+    }
+    float h[8];
+    union { __nv_bfloat162 b[4]; uint4 u; } ph, pl;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = to_tf32(v[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ph.b[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      pl.b[k] = __floats2bfloat162_rn(v[2 * k] - h[2 * k], v[2 * k + 1] - h[2 * k + 1]);
+    }
+    float* hp = hi + r * ld + c;
+    *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(h16 + r * ld + c) = ph.u;
+    *reinterpret_cast<uint4*>(l16 + r * ld + c) = pl.u;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -750,6 +923,24 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
   return 0;
 }
 
+// bf16 plane.  K-major [rows, K] (pitch ld): box {BK k, box_rows}, 64-byte swizzle (a row of the box
+// is 32 bf16 = 64 B).  MN-major [K, rows] (pitch ld): box {64 mn, BK k}, 128-byte swizzle.
+static int make_map16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                      bool mn_major) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) TNN_FAIL("mixed GEMM: bf16 plane must be 16-byte aligned");
+  if (ld % 8 != 0) TNN_FAIL("mixed GEMM: bf16 plane pitch must be a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 64 : BK), (cuuint32_t)(mn_major ? BK : box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TNN_FAIL("cuTensorMapEncodeTiled (bf16) failed with code " + std::to_string((int)r));
+  return 0;
+}
+
 constexpr int DEFAULT_CG = 2;  // CTA pairs: measured 0.98 ms vs 1.10 ms per 8192x4096x4096 product
 static unsigned int* g_tile_flags = nullptr;   // split-K arrival counters
 constexpr int MAX_FLAG_TILES = 1 << 16;
@@ -757,30 +948,47 @@ static int g_group_m = 1;                      // tile rasterisation group; meas
                                                // 1 -> 0.95 ms, 4 -> 0.96-1.04, 8 -> 1.10, 16 -> 1.08
 static int g_force_ksplit = 0;                 // 0 = auto (tail split), 1 = off, 2/4 = every tile (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
-static bool g_attr_set[3][2][2] = {};
+static bool g_attr_set[3][2][2][2] = {};
 
 struct ActOut {
   float* out = nullptr;   // relu(D), pitch ldd
   float* hi = nullptr;    // tf32 planes of relu(D), pitch ld
-  float* lo = nullptr;
+  float* lo = nullptr;    // MIX: the bf16(x) plane
+  void* l16 = nullptr;    // MIX: the bf16(x - hi) plane
   int64_t ld = 0;
   const float* mask_src = nullptr;   // when set: out = D * (mask_src >= 0) instead of relu(D)
 };
 
-template <int CG, bool A_MN, bool B_MN>
-static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_lo, int64_t lda,
-                       const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
+// planes: MIX = false -> (hi, lo) tf32 planes, l16 unused; MIX = true -> (hi tf32, h16, l16)
+struct Planes {
+  const float* hi;
+  const void* lo;     // tf32 lo plane, or the bf16(x) plane
+  const void* l16;    // bf16(x - hi) plane (MIX only)
+  int64_t ld;
+};
+
+template <int CG, bool A_MN, bool B_MN, bool MIX>
+static int launch_gemm(float* D, int64_t ldd, const Planes& a, const Planes& b, int64_t M, int64_t N,
                        int64_t K, const float* bias, int flags, const ActOut& act) {
   using C = Cfg<CG>;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (make_map(&ma_hi, a_hi, M, K, lda, ROWS_A, A_MN)) return 1;
-  if (make_map(&ma_lo, a_lo, M, K, lda, ROWS_A, A_MN)) return 1;
-  if (make_map(&mb_hi, b_hi, N, K, ldb, C::ROWS_B, B_MN)) return 1;
-  if (make_map(&mb_lo, b_lo, N, K, ldb, C::ROWS_B, B_MN)) return 1;
-  auto kern = gemm_tf32x3_kernel<CG, A_MN, B_MN>;
-  if (!g_attr_set[CG][A_MN][B_MN]) {
+  CUtensorMap ma_hi, ma_lo, ma_l16, mb_hi, mb_lo, mb_l16;
+  if (make_map(&ma_hi, a.hi, M, K, a.ld, ROWS_A, A_MN)) return 1;
+  if (make_map(&mb_hi, b.hi, N, K, b.ld, C::ROWS_B, B_MN)) return 1;
+  if constexpr (MIX) {
+    if (make_map16(&ma_lo, a.lo, M, K, a.ld, ROWS_A, A_MN)) return 1;
+    if (make_map16(&ma_l16, a.l16, M, K, a.ld, ROWS_A, A_MN)) return 1;
+    if (make_map16(&mb_lo, b.lo, N, K, b.ld, C::ROWS_B, B_MN)) return 1;
+    if (make_map16(&mb_l16, b.l16, N, K, b.ld, C::ROWS_B, B_MN)) return 1;
+  } else {
+    if (make_map(&ma_lo, (const float*)a.lo, M, K, a.ld, ROWS_A, A_MN)) return 1;
+    if (make_map(&mb_lo, (const float*)b.lo, N, K, b.ld, C::ROWS_B, B_MN)) return 1;
+    ma_l16 = ma_lo;
+    mb_l16 = mb_lo;
+  }
+  auto kern = gemm_tf32x3_kernel<CG, A_MN, B_MN, MIX>;
+  if (!g_attr_set[CG][A_MN][B_MN][MIX]) {
     TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    g_attr_set[CG][A_MN][B_MN] = true;
+    g_attr_set[CG][A_MN][B_MN][MIX] = true;
   }
   const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
   const int max_groups = ctx().sm_count / CG;
@@ -829,8 +1037,8 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(1);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m,
-                              act.out, act.hi, act.lo, act.ld, act.mask_src));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, ma_l16, mb_hi, mb_lo, mb_l16, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m,
+                              act.out, act.hi, act.lo, (__nv_bfloat16*)act.l16, act.ld, act.mask_src));
   ctx().launches++;
   prof_end(1);
   return 0;
@@ -841,17 +1049,51 @@ static int launch_gemm(float* D, int64_t ldd, const float* a_hi, const float* a_
 
 using namespace tnn;
 
-template <int CG>
-static int launch_by_layout(int layout, float* D, int64_t ldd, const float* a_hi, const float* a_lo,
-                            int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, int64_t M,
-                            int64_t N, int64_t K, const float* bias, int flags,
-                            const tnn::tc::ActOut& act) {
+template <int CG, bool MIX>
+static int launch_by_layout(int layout, float* D, int64_t ldd, const tnn::tc::Planes& a,
+                            const tnn::tc::Planes& b, int64_t M, int64_t N, int64_t K, const float* bias,
+                            int flags, const tnn::tc::ActOut& act) {
   switch (layout & 3) {
-    case 0: return tnn::tc::launch_gemm<CG, false, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
-    case 1: return tnn::tc::launch_gemm<CG, true, false>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
-    case 2: return tnn::tc::launch_gemm<CG, false, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
-    default: return tnn::tc::launch_gemm<CG, true, true>(D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+    case 0: return tnn::tc::launch_gemm<CG, false, false, MIX>(D, ldd, a, b, M, N, K, bias, flags, act);
+    case 1: return tnn::tc::launch_gemm<CG, true, false, MIX>(D, ldd, a, b, M, N, K, bias, flags, act);
+    case 2: return tnn::tc::launch_gemm<CG, false, true, MIX>(D, ldd, a, b, M, N, K, bias, flags, act);
+    default: return tnn::tc::launch_gemm<CG, true, true, MIX>(D, ldd, a, b, M, N, K, bias, flags, act);
   }
+}
+
+static int gemm_common(const char* who, bool mix, float* D, int64_t ldd, const tnn::tc::Planes& a,
+                       const tnn::tc::Planes& b, int64_t M, int64_t N, int64_t K, const float* bias,
+                       int flags, int layout, const tnn::tc::ActOut& act_in) {
+  TNN_REQUIRE_INIT();
+  if (M <= 0 || N <= 0) return 0;
+  if (K <= 0) TNN_FAIL(std::string(who) + ": K must be positive");
+  if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) TNN_FAIL(std::string(who) + ": extent above int32");
+  if (tc::get_encode_fn()) return 1;
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("TNN_GEMM_CG");
+    if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
+    const char* ks = getenv("TNN_GEMM_KSPLIT");
+    if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
+    env_read = true;
+  }
+  tc::ActOut act = act_in;
+  if (act.out) {
+    const int64_t need = mix ? 8 : 4;
+    if ((act.hi == nullptr) != (act.lo == nullptr)) TNN_FAIL(std::string(who) + ": activation planes come together");
+    if (mix && (act.hi == nullptr) != (act.l16 == nullptr)) TNN_FAIL(std::string(who) + ": activation planes come together");
+    if (act.hi && (act.ld % need != 0 || act.ld < N)) TNN_FAIL(std::string(who) + ": ld_act must be >= N and suitably padded");
+    if (flags & 2) TNN_FAIL(std::string(who) + ": act_out and the relu-in-place flag are exclusive");
+  } else {
+    act = tc::ActOut();
+  }
+  const int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
+  if (mix) {
+    if (cg == 2) return launch_by_layout<2, true>(layout, D, ldd, a, b, M, N, K, bias, flags, act);
+    return launch_by_layout<1, true>(layout, D, ldd, a, b, M, N, K, bias, flags, act);
+  }
+  if (cg == 2) return launch_by_layout<2, false>(layout, D, ldd, a, b, M, N, K, bias, flags, act);
+  return launch_by_layout<1, false>(layout, D, ldd, a, b, M, N, K, bias, flags, act);
 }
 
 extern "C" {
@@ -896,34 +1138,45 @@ int tnn_gemm_tf32x3(float* D, int64_t ldd, const float* a_hi, const float* a_lo,
                     const float* b_hi, const float* b_lo, int64_t ldb, int64_t M, int64_t N,
                     int64_t K, const float* bias, int flags, int layout, float* act_out,
                     float* act_hi, float* act_lo, int64_t ld_act, const float* mask_src) {
-  TNN_REQUIRE_INIT();
-  if (M <= 0 || N <= 0) return 0;
-  if (K <= 0) TNN_FAIL("tnn_gemm_tf32x3: K must be positive");
-  if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) TNN_FAIL("tnn_gemm_tf32x3: extent above int32");
-  if (tc::get_encode_fn()) return 1;
-  static bool env_read = false;
-  if (!env_read) {
-    const char* e = getenv("TNN_GEMM_CG");
-    if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
-    const char* ks = getenv("TNN_GEMM_KSPLIT");
-    if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
-    env_read = true;
-  }
+  tc::Planes a{a_hi, a_lo, nullptr, lda}, b{b_hi, b_lo, nullptr, ldb};
   tc::ActOut act;
-  if (act_out) {
-    if ((act_hi == nullptr) != (act_lo == nullptr)) TNN_FAIL("tnn_gemm_tf32x3: act_hi/act_lo come in pairs");
-    if (act_hi && (ld_act % 4 != 0 || ld_act < N)) TNN_FAIL("tnn_gemm_tf32x3: ld_act must be >= N and a multiple of 4");
-    if (flags & 2) TNN_FAIL("tnn_gemm_tf32x3: act_out and the relu-in-place flag are exclusive");
-    act.mask_src = mask_src;
-    act.out = act_out;
-    act.hi = act_hi;
-    act.lo = act_lo;
-    act.ld = ld_act;
-  }
-  int cg = tc::g_force_cg ? tc::g_force_cg : tc::DEFAULT_CG;
-  if (cg == 2)
-    return launch_by_layout<2>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
-  return launch_by_layout<1>(layout, D, ldd, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, bias, flags, act);
+  act.out = act_out;
+  act.hi = act_hi;
+  act.lo = act_lo;
+  act.ld = ld_act;
+  act.mask_src = mask_src;
+  return gemm_common("tnn_gemm_tf32x3", false, D, ldd, a, b, M, N, K, bias, flags, layout, act);
+}
+
+int tnn_split_tf32_bf16(const float* x, int64_t R, int64_t C, float* hi, void* h16, void* l16,
+                        int64_t ld) {
+  TNN_REQUIRE_INIT();
+  if (R <= 0 || C <= 0) return 0;
+  if (!hi || !h16 || !l16) TNN_FAIL("tnn_split_tf32_bf16: all three planes are required");
+  if (ld % 8 != 0 || ld < C) TNN_FAIL("tnn_split_tf32_bf16: ld must be >= C and a multiple of 8");
+  const int vec_in = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  prof_begin(3);
+  tc::split_mix_kernel<<<ew_grid(R * (ld / 8), 256), 256, 0, ctx().stream>>>(
+      x, R, C, hi, (__nv_bfloat16*)h16, (__nv_bfloat16*)l16, ld, vec_in);
+  TNN_POST_LAUNCH();
+  prof_end(3);
+  return 0;
+}
+
+int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd, const float* a_hi, const void* a_h16, const void* a_l16,
+                         int64_t lda, const float* b_hi, const void* b_h16, const void* b_l16,
+                         int64_t ldb, int64_t M, int64_t N, int64_t K, const float* bias, int flags,
+                         int layout, float* act_out, float* act_hi, void* act_h16, void* act_l16,
+                         int64_t ld_act, const float* mask_src) {
+  tc::Planes a{a_hi, a_h16, a_l16, lda}, b{b_hi, b_h16, b_l16, ldb};
+  tc::ActOut act;
+  act.out = act_out;
+  act.hi = act_hi;
+  act.lo = (float*)act_h16;
+  act.l16 = act_l16;
+  act.ld = ld_act;
+  act.mask_src = mask_src;
+  return gemm_common("tnn_gemm_tf32_bf16x2", true, D, ldd, a, b, M, N, K, bias, flags, layout, act);
 }
 
 }  // extern "C"

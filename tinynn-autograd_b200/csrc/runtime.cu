@@ -45,6 +45,24 @@ struct Pool {
 };
 static Pool g_pool;
 
+// A captured step (tnn_graph_*) replays kernels that have the addresses of their temporaries baked
+// in.  Every block handed out while the capture runs therefore belongs to the graph: it can be
+// reused by later allocations of the SAME capture (stream order inside the graph is the same as
+// it was eagerly), but it never goes back to the general free lists until the graph is destroyed.
+struct Graph {
+  int id = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<void*> blocks;                                   // every block the capture touched
+  std::unordered_map<size_t, std::vector<void*>> free_lists;   // only meaningful while capturing
+  size_t nodes = 0, kernel_nodes = 0;
+};
+static Graph* g_capture = nullptr;                              // capture in progress, if any
+static std::unordered_map<void*, Graph*> g_block_graph;         // block -> owning graph
+static int g_graph_ids = 0;
+static int g_live_graphs = 0;
+static std::vector<void*> g_retired_scratch;                    // old scratch a live graph may still name
+
 static size_t round_size(size_t n) {
   if (n == 0) n = 1;
   if (n <= (1u << 20)) return (n + 511) & ~size_t(511);
@@ -66,10 +84,14 @@ static void pool_release_all_free_locked() {
 int get_scratch(size_t nbytes, void** out) {
   Context& c = ctx();
   if (nbytes > c.scratch_bytes) {
+    if (g_capture)
+      TNN_FAIL("reduction scratch would have to grow during graph capture (run the step once "
+               "eagerly first)");
     // the old scratch may still be read by queued kernels: drain before replacing it
     if (c.scratch) {
       TNN_CUDA(cudaStreamSynchronize(c.stream));
-      TNN_CUDA(cudaFree(c.scratch));
+      if (g_live_graphs > 0) g_retired_scratch.push_back(c.scratch);  // a captured step may name it
+      else TNN_CUDA(cudaFree(c.scratch));
       c.scratch = nullptr;
       c.scratch_bytes = 0;
     }
@@ -159,7 +181,10 @@ int tnn_shutdown(void) {
     g_pool.live.clear();
     g_pool.free_lists.clear();
     g_pool.reserved = g_pool.in_use = 0;
+    g_block_graph.clear();
   }
+  for (void* p : g_retired_scratch) cudaFree(p);
+  g_retired_scratch.clear();
   if (c.scratch) cudaFree(c.scratch);
   if (c.l2_flush_buf) cudaFree(c.l2_flush_buf);
   c.scratch = c.l2_flush_buf = nullptr;
@@ -199,13 +224,29 @@ int tnn_alloc(size_t nbytes, void** out) {
   TNN_REQUIRE_INIT();
   size_t r = round_size(nbytes);
   std::lock_guard<std::mutex> lk(g_pool.mu);
-  auto it = g_pool.free_lists.find(r);
   void* p = nullptr;
+  if (g_capture) {
+    auto git = g_capture->free_lists.find(r);
+    if (git != g_capture->free_lists.end() && !git->second.empty()) {
+      p = git->second.back();
+      git->second.pop_back();
+      g_pool.live[p] = r;
+      g_pool.in_use += r;
+      *out = p;
+      return 0;
+    }
+  }
+  auto it = g_pool.free_lists.find(r);
   if (it != g_pool.free_lists.end() && !it->second.empty()) {
     p = it->second.back();
     it->second.pop_back();
   } else {
     cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess && g_capture) {
+      cudaGetLastError();
+      TNN_FAIL(std::string("tnn_alloc: cudaMalloc(") + std::to_string(r) +
+               ") failed during graph capture: " + cudaGetErrorString(e));
+    }
     if (e != cudaSuccess) {
       // out of memory: drop every cached block (after draining the stream) and retry once
       cudaGetLastError();
@@ -221,6 +262,10 @@ int tnn_alloc(size_t nbytes, void** out) {
     g_pool.owned[p] = r;
     g_pool.reserved += r;
     g_pool.n_malloc++;
+  }
+  if (g_capture) {
+    g_capture->blocks.push_back(p);
+    g_block_graph[p] = g_capture;
   }
   g_pool.live[p] = r;
   g_pool.in_use += r;
@@ -247,6 +292,15 @@ int tnn_free(void* p) {
   size_t r = it->second;
   g_pool.live.erase(it);
   g_pool.in_use -= r;
+  if (!g_block_graph.empty()) {
+    auto og = g_block_graph.find(p);
+    if (og != g_block_graph.end()) {
+      // owned by a captured step: reusable inside that capture only, otherwise parked until
+      // tnn_graph_destroy
+      if (og->second == g_capture) g_capture->free_lists[r].push_back(p);
+      return 0;
+    }
+  }
   g_pool.free_lists[r].push_back(p);
   return 0;
 }
@@ -271,6 +325,8 @@ int tnn_pool_trim(void) {
 int tnn_h2d(void* dst, const void* src, size_t nbytes) {
   TNN_REQUIRE_INIT();
   if (nbytes == 0) return 0;
+  // a captured copy would re-read this (by then dangling) host address at every replay
+  if (g_capture) TNN_FAIL("tnn_h2d: host upload inside a graph capture");
   TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx().stream));
   return 0;
 }
@@ -278,6 +334,7 @@ int tnn_h2d(void* dst, const void* src, size_t nbytes) {
 int tnn_d2h(void* dst, const void* src, size_t nbytes) {
   TNN_REQUIRE_INIT();
   if (nbytes == 0) return 0;
+  if (g_capture) TNN_FAIL("tnn_d2h: host read-back inside a graph capture (nothing has run yet)");
   TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
   TNN_CUDA(cudaStreamSynchronize(ctx().stream));
   return 0;
@@ -398,6 +455,132 @@ int tnn_prof_collect(double* total_ms, uint64_t* n_launches) {
   if (total_ms) *total_ms = tot;
   if (n_launches) *n_launches = g_prof_used.size();
   g_prof_used.clear();
+  return 0;
+}
+
+// ---- captured steps (CUDA graphs) --------------------------------------------------------------
+// The MNIST-shaped training step is ~35 launches of a few microseconds each: issued one by one
+// from Python it is bound by launch overhead.  tnn_graph_begin/end record everything the host
+// queues on the compute stream in between -- kernels, memsets, device copies, NCCL collectives --
+// into a CUDA graph; tnn_graph_launch replays the whole step with one call.
+int tnn_graph_begin(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  if (g_capture) TNN_FAIL("tnn_graph_begin: a capture is already in progress");
+  if (c.prof_family) TNN_FAIL("tnn_graph_begin: per-kernel profiling is on (tnn_prof_enable(0) first)");
+  Graph* g = new Graph();
+  g->id = ++g_graph_ids;
+  cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    delete g;
+    TNN_FAIL(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+  }
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  g_capture = g;
+  return 0;
+}
+
+static void graph_release_blocks_locked(Graph* g) {
+  for (void* p : g->blocks) {
+    g_block_graph.erase(p);
+    if (g_pool.live.find(p) != g_pool.live.end()) continue;  // still held by the host: now ordinary
+    auto ow = g_pool.owned.find(p);
+    if (ow != g_pool.owned.end()) g_pool.free_lists[ow->second].push_back(p);
+  }
+  g->blocks.clear();
+  g->free_lists.clear();
+}
+
+int tnn_graph_end(void** graph_out) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  if (!g_capture) TNN_FAIL("tnn_graph_end: no capture in progress");
+  Graph* g = g_capture;
+  cudaError_t e = cudaStreamEndCapture(c.stream, &g->graph);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_capture = nullptr;
+    g->free_lists.clear();
+  }
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (g->graph) cudaGraphDestroy(g->graph);
+    {
+      std::lock_guard<std::mutex> lk(g_pool.mu);
+      graph_release_blocks_locked(g);
+    }
+    delete g;
+    TNN_FAIL(std::string("graph capture failed: ") + cudaGetErrorString(e));
+  }
+  size_t n = 0;
+  cudaGraphGetNodes(g->graph, nullptr, &n);
+  g->nodes = n;
+  if (n) {
+    std::vector<cudaGraphNode_t> nodes(n);
+    cudaGraphGetNodes(g->graph, nodes.data(), &n);
+    for (auto nd : nodes) {
+      cudaGraphNodeType t;
+      if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) g->kernel_nodes++;
+    }
+  }
+  g_live_graphs++;
+  *graph_out = (void*)g;
+  return 0;
+}
+
+// abandon a capture in progress (the host raised in the middle of the step)
+int tnn_graph_abort(void) {
+  if (!g_capture) return 0;
+  Graph* g = g_capture;
+  cudaGraph_t tmp = nullptr;
+  cudaStreamEndCapture(ctx().stream, &tmp);
+  cudaGetLastError();
+  if (tmp) cudaGraphDestroy(tmp);
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  g_capture = nullptr;
+  graph_release_blocks_locked(g);
+  delete g;
+  return 0;
+}
+
+int tnn_graph_launch(void* graph) {
+  TNN_REQUIRE_INIT();
+  Graph* g = (Graph*)graph;
+  if (!g || !g->exec) TNN_FAIL("tnn_graph_launch: bad graph handle");
+  TNN_CUDA(cudaGraphLaunch(g->exec, ctx().stream));
+  ctx().launches += g->kernel_nodes;
+  return 0;
+}
+
+int tnn_graph_info(void* graph, size_t* n_nodes, size_t* n_kernel_nodes, size_t* n_blocks) {
+  Graph* g = (Graph*)graph;
+  if (!g) TNN_FAIL("tnn_graph_info: bad graph handle");
+  if (n_nodes) *n_nodes = g->nodes;
+  if (n_kernel_nodes) *n_kernel_nodes = g->kernel_nodes;
+  if (n_blocks) *n_blocks = g->blocks.size();
+  return 0;
+}
+
+int tnn_graph_destroy(void* graph) {
+  Graph* g = (Graph*)graph;
+  if (!g) return 0;
+  if (!ctx().inited) {  // after shutdown everything is already gone
+    delete g;
+    return 0;
+  }
+  cudaStreamSynchronize(ctx().stream);  // a replay may still be running
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    graph_release_blocks_locked(g);
+  }
+  delete g;
+  if (--g_live_graphs == 0) {
+    for (void* p : g_retired_scratch) cudaFree(p);
+    g_retired_scratch.clear();
+  }
   return 0;
 }
 
