@@ -327,19 +327,25 @@ def run_b200_arm(args, cfg):
     if gemm_n:
         per_launch_flops = flops_step * args.steps / gemm_n
         achieved = per_launch_flops / (gemm_ms / gemm_n * 1e-3) / 1e12
-        peak = peaks["bf16_sustained"] / 6.0   # TF32 = bf16/2, three MMAs per algorithmic MMA
+        # tensor-pipe cost of one algorithmic MMA, in bf16-MMA equivalents (a TF32 MMA costs two):
+        #   mix    : 1 TF32 + 2 BF16 = 4        tf32x3 : 3 TF32 = 6
+        mix = be.TC_SPLIT == "mix"
+        cost = 4.0 if mix else 6.0
+        peak = peaks["bf16_sustained"] / cost
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tpath):   # dram bytes per launch from the committed ncu --set full capture
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
-                    "frac_of_burst": achieved / (peaks["bf16_burst"] / 6.0),
-                    "frac_of_nominal_tf32": achieved / 375.0,
-                    "kernel": "gemm_tf32x3_kernel", "launches": int(gemm_n),
+                    "frac_of_burst": achieved / (peaks["bf16_burst"] / cost),
+                    "frac_of_nominal": achieved / (2250.0 / cost),
+                    "kernel": "gemm_tf32x3_kernel<MIX=%d>" % int(mix), "launches": int(gemm_n),
                     "avg_launch_ms": gemm_ms / gemm_n, "share_of_step": gemm_ms / ms,
-                    "peak_source": "%s bf16 sustained %.1f TFLOP/s / 6 (3xTF32)" % (
-                        peaks["source"], peaks["bf16_sustained"])}
+                    "split": be.TC_SPLIT,
+                    "peak_source": "%s bf16 sustained %.1f TFLOP/s / %d (%s)" % (
+                        peaks["source"], peaks["bf16_sustained"], int(cost),
+                        "1 TF32 + 2 BF16 MMAs per algorithmic MMA" if mix else "3 TF32 MMAs per algorithmic MMA")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -356,7 +362,9 @@ def run_b200_arm(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.global_batch else "weak",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)",
+            "vs_baseline": None,
+            "dtype": "f32 (tensor-core GEMMs: %s, fp32 accumulate)" % (
+                "tf32 main term + bf16 cross terms" if be.TC_SPLIT == "mix" else "3xTF32"),
             "data": "synthetic",
             "config": dict(make_config(cfg, B, world),
                            step_mode="cuda_graph_replay" if use_graph else "eager_launches"),
