@@ -92,7 +92,7 @@ _SIGNATURES = {
     "tnn_gather_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_scatter_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_simt": [_c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64,
-                      _c_i64, _c_i64, _c_vp, _c_int, _c_vp],
+                      _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_vp],
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                         _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -109,6 +109,7 @@ _SIGNATURES = {
     "tnn_ce_stats": [_c_int, _c_vp, _c_i64, _c_i64, _c_vp],
     "tnn_ce_merge_stats": [_c_int, _c_vp, _c_vp, _c_int],
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
+    "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -324,6 +325,18 @@ def full(shape, value, dtype):
         if _lib.tnn_fill(_DT_CODE[out.dtype], out.ptr, float(value), out.size):
             _raise("tnn_fill")
     return out
+
+
+_ONES = {}
+
+
+def ones_scalar(dtype):
+    """a persistent 0-d array holding 1.0 (the default seed of backward()); never written again"""
+    dtype = np.dtype(dtype)
+    one = _ONES.get(dtype)
+    if one is None:
+        one = _ONES[dtype] = full((), 1.0, dtype)
+    return one
 
 
 def zeros(shape, dtype):
@@ -769,14 +782,13 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         return out
     a_rs, a_cs = (1, a.shape[1]) if ta else (a.shape[1], 1)
     b_rs, b_cs = (1, b.shape[1]) if tb else (b.shape[1], 1)
-    fused_act = act and mask_src is None
+    if mask_src is not None and mask_src.dtype != dt:
+        mask_src = astype(mask_src, dt)
     if _lib.tnn_gemm_simt(_DT_CODE[dt], out.ptr, N, a.ptr, a_rs, a_cs, b.ptr, b_rs, b_cs, M, N, K,
                           bias.ptr if bias is not None else None, flags & 1,
-                          act_out.ptr if fused_act else None):
+                          act_out.ptr if act else None,
+                          mask_src.ptr if (act and mask_src is not None) else None):
         _raise("tnn_gemm_simt")
-    if act and mask_src is not None:   # SIMT path: the mask is a separate (tiny) launch
-        if _lib.tnn_relu_bwd(_DT_CODE[dt], act_out.ptr, out.ptr, mask_src.ptr, out.size):
-            _raise("tnn_relu_bwd")
     if relu:
         if _lib.tnn_relu_fwd(_DT_CODE[dt], out.ptr, out.ptr, out.size):
             _raise("tnn_relu_fwd")
@@ -825,6 +837,20 @@ def ce_loss(z, y, stats, m_global):
                         float(m_global), q.ptr, loss.ptr):
         _raise("tnn_ce_loss")
     return loss, q
+
+
+def ce_small_ok(B, C):
+    return B <= 2048 and B * C <= 16384
+
+
+def ce_fwd_small(z, y, m_global):
+    """stats, loss and q of a small logits matrix in one launch"""
+    B, C = z.shape
+    stats, q, loss = empty((2,), z.dtype), empty((B,), z.dtype), empty((), z.dtype)
+    if _lib.tnn_ce_fwd_small(_DT_CODE[z.dtype], z.ptr, _DT_CODE[y.dtype], y.ptr, B, C,
+                             float(m_global), stats.ptr, q.ptr, loss.ptr):
+        _raise("tnn_ce_fwd_small")
+    return stats, loss, q
 
 
 def ce_bwd(z, y, stats, q, m_global, g):

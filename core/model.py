@@ -233,6 +233,8 @@ class _CapturedStep(object):
         self.plist = model._param_list()
         opt = model.optimizer
         self.graph = be.StepGraph()
+        for dt in (be.F32, be.F64):
+            be.ones_scalar(dt)       # shared constants must exist (and hold 1.0) before recording
         opt._hyper_dev = self.hyper
         try:
             with self.graph.capture():

@@ -16,9 +16,11 @@ import os
 
 import core._backend as be
 
-# ReLU-backward mask fused into the dX GEMM epilogue.  Correct and bit-identical (tested), 6 fewer
-# launches per wide-MLP step, but the GEMM epilogue is on the tensor pipe's critical path and the
-# A/B measurement showed no gain (12.79 vs 12.84 ms/step), so it is opt-in.
+# ReLU-backward mask fused into the dX GEMM epilogue.  Correct and bit-identical (tested).  On the
+# tensor-core path it is 6 fewer launches per wide-MLP step, but the step is power-bound and the
+# A/B measurements showed no gain (12.79 vs 12.84 ms/step; 11.58 vs 11.58 with the mixed split), so
+# there it is opt-in.  On the SIMT path (MNIST-sized layers, launch-bound) it is always on: one
+# launch less per hidden layer.
 FUSE_RELU_BWD = os.environ.get("TNN_FUSE_RELU_BWD", "0") != "0"
 
 
@@ -476,10 +478,12 @@ def _dense_node(ts_x, ts_w, ts_b, values):
     """graph node of x@w+b: dX = g@w.T, dW = x.T@g, db = column sum of g"""
     x, w = ts_x._data, ts_w._data
 
-    pre = getattr(ts_x, "_relu_pre", None) if FUSE_RELU_BWD else None   # x = relu(pre) from dense_relu_
+    pre = getattr(ts_x, "_relu_pre", None)   # x = relu(pre) from dense_relu_
 
     def grad_fn_x(grad, out=None, accumulate=False):
-        if pre is not None and out is None and pre.dtype == grad.dtype:
+        fuse_mask = pre is not None and out is None and pre.dtype == grad.dtype and (
+            FUSE_RELU_BWD or not be.use_tensor_cores(grad.shape[0], w.shape[0], w.shape[1], grad.dtype))
+        if fuse_mask:
             # x came out of a ReLU: the dX launch also applies that ReLU's mask and leaves the masked
             # gradient (with its tf32 planes) on the side for the ReLU node, which then has no
             # kernel of its own to run.  dX itself (dL/dx, unmasked) is returned as always.
@@ -544,12 +548,15 @@ def softmax_ce_(ts_logits, ts_labels):
     B, C = z.shape
     world = dist.world_size()
     m_global = B * world
-    stats = be.ce_stats(z)
-    if world > 1:
-        stats = dist.merge_ce_stats(stats)
-    loss, q = be.ce_loss(z, y, stats, m_global)
-    if world > 1:
-        dist.allreduce_sum(loss)
+    if world == 1 and be.ce_small_ok(B, C):
+        stats, loss, q = be.ce_fwd_small(z, y, m_global)     # one launch instead of three
+    else:
+        stats = be.ce_stats(z)
+        if world > 1:
+            stats = dist.merge_ce_stats(stats)
+        loss, q = be.ce_loss(z, y, stats, m_global)
+        if world > 1:
+            dist.allreduce_sum(loss)
 
     def grad_fn(grad):
         return be.ce_bwd(z, y, stats, q, m_global, grad)

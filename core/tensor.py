@@ -292,7 +292,10 @@ class Tensor(object):
     def backward(self, grad=None):
         assert self.requires_grad, "Call backward() on a non-requires-grad tensor."
         if grad is None:
-            seed = be.full(self._data.shape, 1.0, self._data.dtype)
+            if self._data.shape == ():
+                seed = be.ones_scalar(self._data.dtype)      # shared constant, no launch
+            else:
+                seed = be.full(self._data.shape, 1.0, self._data.dtype)
         else:
             seed = self._coerce_grad(grad)
 

@@ -170,10 +170,14 @@ int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev
 /* ---- GEMM (ops.py:150-163 dot_: A@B, grad@B.T, A.T@grad) ----------------------------------- */
 /* SIMT path, any shape, f32/f64.  C[M,N] (ldc) = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C).
  * A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]; flags bit0 = accumulate into C.
- * act_out (may be NULL, pitch ldc) additionally receives ReLU(C): Dense + ReLU in one launch. */
+ * act_out (may be NULL, pitch ldc) additionally receives ReLU(C): Dense + ReLU in one launch; with
+ * mask_src (pitch ldc) it receives C * (mask_src >= 0) instead: the dX product and the ReLU
+ * backward of the layer below (ops.py:156-157 + 342-343) in one launch.
+ * Products with few 32x32 tiles and K >= 128 run as a thread-block cluster along K (partials are
+ * folded in rank order over distributed shared memory: deterministic, no scratch). */
 int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs, int64_t a_cs,
                   const void* B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                  const void* bias, int flags, void* act_out);
+                  const void* bias, int flags, void* act_out, const void* mask_src);
 /* fp32 -> (hi, lo) tf32 planes for the 3xTF32 tensor-core GEMM.  x is [R, C] row-major (ld = C).
  * plain planes  hi/lo  : [R, ldp]  (ldp >= C, multiple of 4)   -- may be NULL
  * transposed    hiT/loT: [C, ldt]  (ldt >= R, multiple of 4)   -- may be NULL */
@@ -243,6 +247,10 @@ int tnn_ce_stats(int dtype, const void* z, int64_t B, int64_t C, void* stats_dev
 int tnn_ce_merge_stats(int dtype, void* stats_out_dev, const void* stats_all_dev, int n_ranks);
 int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                 const void* stats_dev, double m_global, void* q_dev, void* loss_dev);
+/* stages 1 + 2 in ONE single-CTA launch for small logits (B <= 2048, B*C <= 16384: the
+ * examples/mnist 128 x 10 case), single process only; same arithmetic and order as the staged path */
+int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+                     double m_global, void* stats_dev, void* q_dev, void* loss_dev);
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                const void* stats_dev, const void* q_dev, double m_global, const void* g_dev);
 

@@ -58,6 +58,31 @@ def main():
             err = np.max(np.abs(p - rp.values)) / max(np.max(np.abs(rp.values)), 1e-30)
             assert err <= 1e-5, err
         print("DIST_OK world=%d losses=%s" % (world, losses))
+    # the captured step (CUDA graph holding the NCCL all-gather / all-reduces) must reproduce the
+    # eager data-parallel loop bit for bit
+    def fresh():
+        np.random.seed(1)
+        n = Net([Dense(24, num_in=D), ReLU(), Dense(C, num_in=24)])
+        return n, Model(net=n, loss=SoftmaxCrossEntropyLoss(), optimizer=SGD(lr=0.5))
+
+    xs, ys = Tensor(x[lo:hi]), Tensor(labels[lo:hi])
+    net_e, model_e = fresh()
+    eager = []
+    for _ in range(6):
+        model_e.zero_grad()
+        loss = model_e.loss.loss(model_e.forward(xs), ys)
+        loss.backward()
+        model_e.step()
+        eager.append(float(loss.values))
+    net_g, model_g = fresh()
+    replayed = [float(model_g.train_step(xs, ys).values) for _ in range(6)]
+    assert any(hasattr(v, "graph") for v in model_g._captured.values()), "step was not captured"
+    assert eager == replayed, (eager, replayed)
+    for pe, pg in zip(net_e.get_parameters(), net_g.get_parameters()):
+        for k in pe:
+            assert np.array_equal(pe[k].values, pg[k].values)
+    if rank == 0:
+        print("GRAPH_DIST_OK world=%d" % world)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -203,7 +203,8 @@ def test_tf32x3_better_than_plain_tf32(be):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (128, 200, 784), (80, 10, 30), (257, 65, 33), (64, 64, 0)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (128, 200, 784), (80, 10, 30), (257, 65, 33), (64, 64, 0),
+                                   (128, 100, 200), (64, 32, 1000), (30, 30, 4100), (33, 31, 129)])
 def test_simt_gemm(be, dtype, shape):
     M, N, K = shape
     rng = np.random.RandomState(M + N + K)
@@ -219,5 +220,32 @@ def test_simt_gemm(be, dtype, shape):
         at, bt = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)
         assert op_cases.rel_err(be.matmul(be.from_numpy(at), db, ta=True).numpy(), _ref(at, b, True, False, None)) <= tol
         assert op_cases.rel_err(be.matmul(da, be.from_numpy(bt), tb=True).numpy(), _ref(a, bt, False, True, None)) <= tol
+    finally:
+        be.TC_ENABLED = old
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(128, 200, 100), (80, 70, 30), (128, 784, 200), (16, 1000, 24)])
+def test_simt_gemm_fused_outputs(be, dtype, shape):
+    """SIMT path: act=True returns (z, relu(z)); with mask_src (dX form, also through the cluster
+    split-K variant) the second output is z * (mask_src >= 0); repeated runs are bit-identical"""
+    M, N, K = shape
+    rng = np.random.RandomState(M + 3 * N + K)
+    a = rng.standard_normal((M, K)).astype(dtype)
+    bt = rng.standard_normal((N, K)).astype(dtype)
+    pre = rng.standard_normal((M, N)).astype(dtype)
+    pre[0, 0] = 0.0
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    old = be.TC_ENABLED
+    be.TC_ENABLED = False
+    try:
+        da, dbt = be.from_numpy(a), be.from_numpy(bt)
+        ref = a.astype(np.float64) @ bt.astype(np.float64).T
+        z, act = be.matmul(da, dbt, tb=True, act=True)
+        assert op_cases.rel_err(z.numpy(), ref) <= tol
+        assert np.array_equal(act.numpy(), np.maximum(z.numpy(), 0))
+        g, masked = be.matmul(da, dbt, tb=True, act=True, mask_src=be.from_numpy(pre))
+        assert np.array_equal(g.numpy(), z.numpy())
+        assert np.array_equal(masked.numpy(), g.numpy() * (pre >= 0))
     finally:
         be.TC_ENABLED = old

@@ -60,6 +60,25 @@ def test_ce_fused_equals_composed(engine):
         assert op_cases.rel_err(a.grad, b.grad) <= tol
 
 
+@pytest.mark.parametrize("shape", [(128, 10), (80, 10), (1, 1), (2048, 8), (37, 101)])
+@pytest.mark.parametrize("zdt,ydt", [(np.float32, np.float64), (np.float32, np.float32), (np.float64, np.float64)])
+def test_ce_single_launch_forward_equals_staged(shape, zdt, ydt):
+    """small logits: the one-CTA forward (stats + per-row q + loss in one launch) is bit-identical
+    to the staged kernels the large / data-parallel path uses"""
+    import core._backend as be
+    B, C = shape
+    rng = np.random.RandomState(B + C)
+    z = be.from_numpy((rng.standard_normal((B, C)) * 3).astype(zdt))
+    y = be.from_numpy(np.eye(C)[rng.randint(0, C, B)].astype(ydt))
+    assert be.ce_small_ok(B, C)
+    stats1, loss1, q1 = be.ce_fwd_small(z, y, B)
+    stats2 = be.ce_stats(z)
+    loss2, q2 = be.ce_loss(z, y, stats2, B)
+    assert np.array_equal(stats1.numpy(), stats2.numpy())
+    assert np.array_equal(q1.numpy(), q2.numpy())
+    assert np.array_equal(loss1.numpy(), loss2.numpy())
+
+
 def test_ce_soft_labels(engine):
     """general (non one-hot) labels: dL/dz = p - y p / (m q)"""
     Tensor, ops, ce = engine

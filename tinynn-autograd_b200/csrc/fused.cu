@@ -247,6 +247,81 @@ ce_fold_loss_kernel(const T* nll, int64_t B, T m, T* loss) {
   if (threadIdx.x == 0) loss[0] = s / m;
 }
 
+// ---- cross entropy forward, whole thing in one CTA (the examples/mnist shape: 128 x 10) ----------
+// Same arithmetic, in the same order, as ce_stats_small_kernel -> ce_rows_kernel -> ce_fold_loss_kernel
+// (so the value is bit-identical to the three-launch path); 2 launches fewer on a launch-bound step.
+constexpr int CE_SMALL_MAX_ROWS = 2048;
+// 1024 threads.  The two block-wide sums are taken over the first 256 threads only, in the order
+// block_all_reduce uses, so they match the 256-thread staged kernels bit for bit; the per-row pass
+// uses all 32 warps, four rows per warp in flight at once (a row per warp at a time would be a
+// chain of 16 exposed load latencies for the 128-row MNIST batch).
+template <typename T, bool IS_MAX>
+__device__ __forceinline__ T block1024_reduce_first8(T v, T* sm /* >= 32 */) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  T r = sm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = IS_MAX ? m_max(r, sm[i]) : r + sm[i];
+  return r;
+}
+
+template <typename T, typename TY>
+__global__ void __launch_bounds__(1024)
+ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats, T* q, T* loss) {
+  __shared__ T sm[32];
+  __shared__ T nll[CE_SMALL_MAX_ROWS];
+  const int64_t n = B * C;
+  const bool first = threadIdx.x < 256;
+  T mx = -INFINITY;
+  if (first)
+    for (int64_t i = threadIdx.x; i < n; i += 256) mx = m_max(mx, z[i]);
+  mx = block1024_reduce_first8<T, true>(mx, sm);
+  T S = T(0);
+  if (first)
+    for (int64_t i = threadIdx.x; i < n; i += 256) S += m_exp(z[i] - mx);
+  S = block1024_reduce_first8<T, false>(S, sm);
+  if (threadIdx.x == 0) {
+    stats[0] = mx;
+    stats[1] = S;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int RU = 4;
+  for (int64_t r0 = warp; r0 < B; r0 += 32 * RU) {
+    T acc[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int64_t r = r0 + 32 * u;
+      acc[u] = T(0);
+      if (r < B) {
+        const T* zr = z + r * C;
+        const TY* yr = y + r * C;
+        for (int64_t j = lane; j < C; j += 32) {
+          TY yy = yr[j];
+          if (yy != TY(0)) acc[u] += (m_exp(zr[j] - mx) / S) * (T)yy;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int64_t r = r0 + 32 * u;
+      const T a = warp_sum(acc[u]);
+      if (lane == 0 && r < B) {
+        q[r] = a;
+        nll[r] = -m_log(a);
+      }
+    }
+  }
+  __syncthreads();
+  T s = T(0);
+  if (first)
+    for (int64_t i = threadIdx.x; i < B; i += 256) s += nll[i];
+  s = block1024_reduce_first8<T, false>(s, sm);
+  if (threadIdx.x == 0) loss[0] = s / m;
+}
+
 // ---- cross entropy backward ---------------------------------------------------------------------
 // dz_kl = g * ( e_kl/S - (1/m) * y_kl * e_kl / (S * q_k) ),  e = exp(z - M)
 template <typename T, typename TY, bool VEC>
@@ -546,6 +621,26 @@ int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B,
   if (dtype == TNN_F64 && y_dtype == TNN_F32)
     return ce_loss_impl<double, float>((const double*)z, (const float*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev);
   TNN_FAIL("tnn_ce_loss: bad dtype");
+}
+
+int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
+                     double m_global, void* stats_dev, void* q_dev, void* loss_dev) {
+  TNN_REQUIRE_INIT();
+  if (B <= 0 || C <= 0) TNN_FAIL("tnn_ce_fwd_small: empty logits");
+  if (B > CE_SMALL_MAX_ROWS || B * C > 16384) TNN_FAIL("tnn_ce_fwd_small: at most 2048 rows and 16384 logits");
+  cudaStream_t st = ctx().stream;
+  if (dtype == TNN_F32 && y_dtype == TNN_F32)
+    ce_fwd_small_kernel<float, float><<<1, 1024, 0, st>>>((const float*)z, (const float*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev);
+  else if (dtype == TNN_F32 && y_dtype == TNN_F64)
+    ce_fwd_small_kernel<float, double><<<1, 1024, 0, st>>>((const float*)z, (const double*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev);
+  else if (dtype == TNN_F64 && y_dtype == TNN_F64)
+    ce_fwd_small_kernel<double, double><<<1, 1024, 0, st>>>((const double*)z, (const double*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev);
+  else if (dtype == TNN_F64 && y_dtype == TNN_F32)
+    ce_fwd_small_kernel<double, float><<<1, 1024, 0, st>>>((const double*)z, (const float*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev);
+  else
+    TNN_FAIL("tnn_ce_fwd_small: bad dtype");
+  TNN_POST_LAUNCH();
+  return 0;
 }
 
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,

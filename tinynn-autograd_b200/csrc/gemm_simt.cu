@@ -7,15 +7,27 @@
 // C[M,N] = A[M,K] * B[K,N] (+ bias[N]) (+ C), shared-memory tiled, register-blocked, the next
 // K-slab prefetched into registers while the current one is multiplied.  Deterministic: each
 // output element is accumulated by one thread in k order.
+//
+// Few tiles and a deep K (the 128x200x784 first layer of the MNIST MLP: 28 tiles, 13 slabs, each a
+// round trip to L2/HBM -> 30 us on 28 of 148 SMs) run as a thread-block CLUSTER along K: the S CTAs
+// of a cluster each multiply one K slice of the same output tile, park their 32x32 partial in
+// their own shared memory, and CTA 0 adds the partials in rank order over distributed shared
+// memory -- one launch, no scratch buffer, no atomics, a fixed summation order.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tnn {
 
-template <typename T, int BM, int BN, int BK, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+// SPLITK: gridDim.z CTAs (one cluster) share an output tile, CTA z covers k in [z*kslice, ...)
+template <typename T, int BM, int BN, int BK, int TM, int TN, bool SPLITK>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), BM == 32 ? 2 : 1)   // small tiles: two CTAs per SM, so an 8-way K cluster of 28 tiles is one wave
 gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_t a_rs, int64_t a_cs,
                  const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                 const T* __restrict__ bias, int flags, T* __restrict__ act_out) {
+                 const T* __restrict__ bias, int flags, T* __restrict__ act_out,
+                 const T* __restrict__ mask_src, int64_t kslice) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_PER = (BM * BK) / NT;
   constexpr int B_PER = (BK * BN) / NT;
@@ -72,13 +84,22 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
     }
   };
 
-  load_tiles(0);
-  for (int64_t k0 = 0; k0 < K; k0 += BK) {
+  int64_t k_begin = 0;
+  if constexpr (SPLITK) {
+    // this CTA's K slice; operands beyond it read as zero through the `gk < K` guard
+    k_begin = (int64_t)blockIdx.z * kslice;
+    const int64_t k_end = k_begin + kslice < K ? k_begin + kslice : K;
+    K = k_end > k_begin ? k_end : k_begin;
+  }
+  load_tiles(k_begin);
+  for (int64_t k0 = k_begin; k0 < K; k0 += BK) {
     store_tiles();
     __syncthreads();
     if (k0 + BK < K) load_tiles(k0 + BK);
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
+    // only as deep as this slab really is (a 30-deep MNIST product must not multiply 98 zeros)
+    const int depth = (K - k0 < BK) ? (int)(K - k0) : BK;
+#pragma unroll 8
+    for (int kk = 0; kk < depth; ++kk) {
       T a[TM], b[TN];
 #pragma unroll
       for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
@@ -92,6 +113,44 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
     __syncthreads();
   }
 
+  if constexpr (SPLITK) {
+    // partial tile -> own shared memory; CTA 0 folds the cluster's partials in rank order
+    static_assert(BK >= BN, "the partial tile reuses the As slab");
+    cg::cluster_group cluster = cg::this_cluster();
+    T (*part)[BM + 1] = As;    // As is [BK][BM+1]: rows 0..BN-1 hold the BN x BM partial (BK >= BN)
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) part[tx * TN + j][ty * TM + i] = acc[i][j];
+    cluster.sync();
+    if (blockIdx.z == 0) {
+      // all remote loads are issued before the first add (one DSMEM latency, not S-1 of them);
+      // the adds then run in rank order
+      const unsigned S = gridDim.z;
+      T pv[7][TM][TN];
+#pragma unroll
+      for (unsigned r = 1; r < 8; ++r) {
+        if (r < S) {
+          T (*peer)[BM + 1] = reinterpret_cast<T (*)[BM + 1]>(cluster.map_shared_rank(&As[0][0], r));
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) pv[r - 1][i][j] = peer[tx * TN + j][ty * TM + i];
+        }
+      }
+#pragma unroll
+      for (unsigned r = 1; r < 8; ++r) {
+        if (r < S) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] += pv[r - 1][i][j];
+        }
+      }
+    }
+    cluster.sync();            // peers keep their shared memory alive until CTA 0 has read it
+    if (blockIdx.z != 0) return;
+  }
   const bool accumulate = flags & 1;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -105,7 +164,12 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
       if (bias) v += bias[gn];
       if (accumulate) v += C[gm * ldc + gn];
       C[gm * ldc + gn] = v;
-      if (act_out) act_out[gm * ldc + gn] = v < T(0) ? T(0) : v;   // fused ReLU output
+      if (act_out) {
+        // fused ReLU output, or (backward form) the ReLU gradient mask of ops.py:336-343 applied
+        // to this dX: act = v * (pre-activation >= 0)
+        if (mask_src) act_out[gm * ldc + gn] = mask_src[gm * ldc + gn] >= T(0) ? v : v * T(0);
+        else act_out[gm * ldc + gn] = v < T(0) ? T(0) : v;
+      }
     }
   }
 }
@@ -113,7 +177,7 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
 template <typename T>
 static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
                           int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                          const T* bias, int flags, T* act_out) {
+                          const T* bias, int flags, T* act_out, const T* mask_src) {
   if (M <= 0 || N <= 0) return 0;
   cudaStream_t st = ctx().stream;
   prof_begin(2);
@@ -121,13 +185,42 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
   if (tiles64 >= ctx().sm_count) {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
     if (grid.y > 65535) TNN_FAIL("tnn_gemm_simt: M too large for the SIMT path");
-    gemm_simt_kernel<T, 64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
+    gemm_simt_kernel<T, 64, 64, 16, 4, 4, false><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, 0);
   } else {
     // few CTAs: the K loop is a chain of exposed global-load latencies (measured 53 us for the
     // 128x200x784 first MNIST layer with 16-wide K slabs), so the small-tile variant takes 64-wide
     // slabs: 4x fewer round trips, 8 loads in flight per thread
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
-    gemm_simt_kernel<T, 32, 32, 64, 2, 2><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out);
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    // One slab per CTA is one exposed load latency instead of a chain of them, so the slab is as
+    // deep as shared memory allows (128 k for float, 64 for double) and, when the tiles leave most
+    // SMs idle, K is cut across a cluster of S CTAs (S <= 8, the portable cluster size) until a
+    // slice fits one slab.
+    constexpr int SBK = sizeof(T) == 4 ? 128 : 64;
+    int64_t S = 1;
+    while (S < 8 && tiles * (S * 2) <= 2 * (int64_t)ctx().sm_count && ceil_div(K, S) > SBK) S *= 2;
+    if (S > 1 && grid.y <= 65535) {
+      grid.z = (unsigned)S;
+      const int64_t kslice = ceil_div(K, S);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = (unsigned)S;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_simt_kernel<T, 32, 32, SBK, 2, 2, true>, C, ldc, A, a_rs, a_cs,
+                                  B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, kslice));
+      ctx().launches++;
+      prof_end(2);
+      return 0;
+    }
+    gemm_simt_kernel<T, 32, 32, SBK, 2, 2, false><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, 0);
   }
   TNN_POST_LAUNCH();
   prof_end(2);
@@ -140,14 +233,18 @@ using namespace tnn;
 
 extern "C" int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs,
                              int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, int64_t M,
-                             int64_t N, int64_t K, const void* bias, int flags, void* act_out) {
+                             int64_t N, int64_t K, const void* bias, int flags, void* act_out,
+                             const void* mask_src) {
   TNN_REQUIRE_INIT();
   if (M < 0 || N < 0 || K < 0) TNN_FAIL("tnn_gemm_simt: negative extent");
+  if (mask_src && !act_out) TNN_FAIL("tnn_gemm_simt: mask_src needs act_out");
   if (dtype == TNN_F32)
     return gemm_simt_impl<float>((float*)C, ldc, (const float*)A, a_rs, a_cs, (const float*)B, b_rs,
-                                 b_cs, M, N, K, (const float*)bias, flags, (float*)act_out);
+                                 b_cs, M, N, K, (const float*)bias, flags, (float*)act_out,
+                                 (const float*)mask_src);
   if (dtype == TNN_F64)
     return gemm_simt_impl<double>((double*)C, ldc, (const double*)A, a_rs, a_cs, (const double*)B,
-                                  b_rs, b_cs, M, N, K, (const double*)bias, flags, (double*)act_out);
+                                  b_rs, b_cs, M, N, K, (const double*)bias, flags, (double*)act_out,
+                                  (const double*)mask_src);
   TNN_FAIL("tnn_gemm_simt: dtype must be TNN_F32 or TNN_F64");
 }

@@ -221,7 +221,9 @@ static int reduce_impl(T* out, const T* x, int64_t outer, int64_t red, int64_t i
   int64_t ncol = vec ? inner / VW : inner;
   int64_t gx = ceil_div(ncol, 32);
   int64_t nsplit = 1;
-  if (gx * outer < target_ctas) {
+  // small inputs (the bias gradients of the MNIST-sized layers: 128 x 200 and below) are bound by
+  // launch latency, not bandwidth: one stage, one launch
+  if (gx * outer < target_ctas && outer * red * inner > (int64_t(1) << 18)) {
     nsplit = std::min<int64_t>(ceil_div(target_ctas, gx * outer), ceil_div(red, 64));
     if (nsplit < 1) nsplit = 1;
   }
