@@ -982,6 +982,16 @@ class Event(object):
             pass
 
 
+_LIVE_GRAPHS = weakref.WeakSet()
+
+
+def destroy_all_graphs():
+    """Recorded steps that contain NCCL collectives keep the communicator referenced: they have to
+    go before the communicator does (core._dist.destroy_process_group calls this)."""
+    for g in list(_LIVE_GRAPHS):
+        g.destroy()
+
+
 class StepGraph(object):
     """A recorded sequence of device work (CUDA graph) that replay() re-issues with one call.
 
@@ -995,11 +1005,14 @@ class StepGraph(object):
     def __init__(self):
         init()
         self.handle = None
+        _LIVE_GRAPHS.add(self)
 
     def capture(self):
         return _Capture(self)
 
     def replay(self):
+        if not self.handle:
+            raise BackendError("this recorded step was destroyed (process group torn down?)")
         if _lib.tnn_graph_launch(self.handle):
             _raise("tnn_graph_launch")
 

@@ -73,6 +73,7 @@ def init_process_group(control_backend="gloo"):
 def destroy_process_group():
     global _world, _rank, _nccl_ready
     if _nccl_ready:
+        be.destroy_all_graphs()   # graphs holding NCCL nodes must not outlive the communicator
         be._lib.tnn_nccl_destroy()
     _world, _rank, _nccl_ready = 1, 0, False
 

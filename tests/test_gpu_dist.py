@@ -30,7 +30,7 @@ def test_two_rank_training_equals_full_batch_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK world=2" in r.stdout
     assert "GRAPH_DIST_OK world=2" in r.stdout
