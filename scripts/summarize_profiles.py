@@ -56,9 +56,17 @@ if os.path.exists(lst):
         f.writelines(lines)
     print("launch list:", len(rows), "launches")
 
+sources = {}
 for rep in sorted(glob.glob(os.path.join(G, "prof_*.ncu-rep"))):
-    name = os.path.basename(rep)[:-8]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    sources[os.path.basename(rep)[:-8]] = ("rep", rep)
+for rawcsv in sorted(glob.glob(os.path.join(G, "prof_*_raw.csv"))):   # converted on the GPU box
+    if os.path.getsize(rawcsv):
+        sources[os.path.basename(rawcsv)[:-8]] = ("csv", rawcsv)
+for name, (kind, path) in sorted(sources.items()):
+    if kind == "rep":
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        raw = open(path).read()
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
         continue
