@@ -118,6 +118,9 @@ _SIGNATURES = {
     "tnn_nccl_destroy": [],
     "tnn_allreduce_sum": [_c_int, _c_vp, _c_i64],
     "tnn_allgather": [_c_int, _c_vp, _c_vp, _c_i64],
+    "tnn_comm_wait_compute": [],
+    "tnn_compute_wait_comm": [],
+    "tnn_allreduce_sum_comm": [_c_int, _c_vp, _c_i64],
     "tnn_nccl_version": [_c_vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["tnn_last_error", "tnn_stream", "tnn_launch_count",

@@ -87,6 +87,40 @@ def allreduce_sum(d):
     return d
 
 
+# Measured on 2 B200s (wide MLP, 30 steps): 1 chunk 11.83 / 11.91 ms per step, 4 chunks 11.89 / 11.92,
+# 8 chunks 11.96 -- the step is power-bound, hiding the optimiser behind the all-reduce buys nothing,
+# so the default is one all-reduce on the compute stream and the pipeline stays a knob.
+ALLREDUCE_CHUNKS = int(os.environ.get("TNN_ALLREDUCE_CHUNKS", "1"))
+MIN_CHUNK_ELEMS = 1 << 20     # pieces below this are not worth a launch of their own
+
+
+def reduce_and_apply(optimizer, param_flat, grad_flat, align=64):
+    """SUM all-reduce of the flat gradient arena pipelined with the fused optimiser: the arena is
+    cut into ALLREDUCE_CHUNKS pieces, piece i+1 is reduced on the comm stream while the optimiser
+    kernel updates piece i on the compute stream.  Every rank cuts identically, so replicas stay
+    bit-identical."""
+    n = grad_flat.size
+    chunks = max(1, min(ALLREDUCE_CHUNKS, n // MIN_CHUNK_ELEMS))
+    if chunks == 1:
+        allreduce_sum(grad_flat)
+        optimizer.apply_fused(param_flat, grad_flat)
+        return
+    per = -(-n // chunks)
+    per = (per + align - 1) // align * align
+    bounds = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
+    if be._lib.tnn_comm_wait_compute():
+        be._raise("tnn_comm_wait_compute")
+    code = be._DT_CODE[grad_flat.dtype]
+    isz = grad_flat.dtype.itemsize
+    hyper = optimizer.step_hyper()
+    for lo, hi in bounds:
+        if be._lib.tnn_allreduce_sum_comm(code, grad_flat.ptr + lo * isz, hi - lo):
+            be._raise("tnn_allreduce_sum_comm")
+        if be._lib.tnn_compute_wait_comm():
+            be._raise("tnn_compute_wait_comm")
+        optimizer.apply_fused_range(param_flat, grad_flat, lo, hi, hyper)
+
+
 def merge_ce_stats(stats):
     """local (max, sum-exp) -> global (max, sum-exp); 2 floats per rank over NCCL"""
     if _world == 1:

@@ -31,6 +31,15 @@ class Model(object):
     def forward(self, inputs):
         return self.net.forward(inputs)
 
+    def predict(self, inputs):
+        """forward pass without an autograd graph (the evaluation at run.py:87-91): activations are
+        released as soon as the next layer has consumed them.  Not in the reference's interface."""
+        import core.ops as ops
+        from core.tensor import Tensor
+        x = inputs if isinstance(inputs, Tensor) else Tensor(inputs)
+        with ops.no_grad():
+            return self.net.forward(x)
+
     # ------------------------------------------------------------------ checkpoint (values only)
     def save(self, path):
         state = [{k: v.values for k, v in layer.items() if v is not None}
@@ -126,8 +135,10 @@ class Model(object):
         if fused and all(p._grad is p._gslot for p in plist):
             a = self._arena
             if dist.world_size() > 1:
-                dist.allreduce_sum(a["g"])  # SUM: 1/m_global is already inside dL/dz
-            self.optimizer.apply_fused(a["p"], a["g"])
+                # SUM (1/m_global is already inside dL/dz), in chunks pipelined with the optimiser
+                dist.reduce_and_apply(self.optimizer, a["p"], a["g"], _ALIGN)
+            else:
+                self.optimizer.apply_fused(a["p"], a["g"])
             for p in plist:
                 p._touch()
                 p._drop_grad()  # reference: `param += step` leaves grad = None (tensor.py:35-38)

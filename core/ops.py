@@ -24,6 +24,26 @@ import core._backend as be
 FUSE_RELU_BWD = os.environ.get("TNN_FUSE_RELU_BWD", "0") != "0"
 
 
+_GRAD_ENABLED = True
+
+
+class no_grad(object):
+    """Context manager: ops run inside it build no autograd graph (outputs have requires_grad =
+    False and hold no references to their inputs), the way an evaluation forward pass wants it
+    (run.py:87-91).  Not part of the reference's interface; Model.predict() uses it."""
+
+    def __enter__(self):
+        global _GRAD_ENABLED
+        self._prev = _GRAD_ENABLED
+        _GRAD_ENABLED = False
+        return self
+
+    def __exit__(self, *exc):
+        global _GRAD_ENABLED
+        _GRAD_ENABLED = self._prev
+        return False
+
+
 def as_tensor(obj, like=None):
     # avoid looping import
     from core.tensor import as_tensor
@@ -32,11 +52,11 @@ def as_tensor(obj, like=None):
 
 def build_binary_ops_tensor(ts1, ts2, grad_fn_ts1, grad_fn_ts2, values):
     """ops.py:12-20"""
-    requires_grad = ts1.requires_grad or ts2.requires_grad
+    requires_grad = (ts1.requires_grad or ts2.requires_grad) and _GRAD_ENABLED
     dependency = []
-    if ts1.requires_grad:
+    if ts1.requires_grad and requires_grad:
         dependency.append(dict(tensor=ts1, grad_fn=grad_fn_ts1))
-    if ts2.requires_grad:
+    if ts2.requires_grad and requires_grad:
         dependency.append(dict(tensor=ts2, grad_fn=grad_fn_ts2))
     tensor_cls = ts1.__class__
     return tensor_cls(values, requires_grad, dependency)
@@ -44,9 +64,9 @@ def build_binary_ops_tensor(ts1, ts2, grad_fn_ts1, grad_fn_ts2, values):
 
 def build_unary_ops_tensor(ts, grad_fn, values):
     """ops.py:23-29"""
-    requires_grad = ts.requires_grad
+    requires_grad = ts.requires_grad and _GRAD_ENABLED
     dependency = []
-    if ts.requires_grad:
+    if requires_grad:
         dependency.append(dict(tensor=ts, grad_fn=grad_fn))
     tensor_cls = ts.__class__
     return tensor_cls(values, requires_grad, dependency)
@@ -505,10 +525,10 @@ def _dense_node(ts_x, ts_w, ts_b, values):
 
     grad_fn_x.supports_out = grad_fn_w.supports_out = grad_fn_b.supports_out = True
     dependency = []
+    requires_grad = (ts_x.requires_grad or ts_w.requires_grad or ts_b.requires_grad) and _GRAD_ENABLED
     for t, fn in ((ts_x, grad_fn_x), (ts_w, grad_fn_w), (ts_b, grad_fn_b)):
-        if t.requires_grad:
+        if t.requires_grad and requires_grad:
             dependency.append(dict(tensor=t, grad_fn=fn))
-    requires_grad = ts_x.requires_grad or ts_w.requires_grad or ts_b.requires_grad
     return ts_x.__class__(values, requires_grad, dependency)
 
 

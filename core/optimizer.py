@@ -71,6 +71,27 @@ class BaseOptimizer(object):
         """param_flat += step(grad_flat), in place, one kernel"""
         self._run(param_flat, None, grad_flat)
 
+    def step_hyper(self):
+        """this step's hyper-parameters (Adam: advances t); a captured step reads them from device"""
+        return self._hyper_dev if self._hyper_dev is not None else self._hyper()
+
+    def apply_fused_range(self, param_flat, grad_flat, lo, hi, hyper):
+        """the fused update on elements [lo, hi) of the flat arenas, with hyper from step_hyper()"""
+        self._ensure_state(grad_flat)
+        n = hi - lo
+        s = [st.view((n,), lo) for st in self._state] + [None, None]
+        be.opt_step(self.opt_code, param_flat.view((n,), lo), None, grad_flat.view((n,), lo),
+                    s[0], s[1], hyper)
+
+    def _ensure_state(self, grad):
+        if self.opt_code is None:
+            raise NotImplementedError
+        if self._state is None:
+            self._state = [be.zeros(grad.shape, grad.dtype) for _ in range(self.n_state)]
+        elif self._state and (self._state[0].size != grad.size or self._state[0].dtype != grad.dtype):
+            raise ValueError("optimizer state was built for %d parameters of %s, got %d of %s"
+                             % (self._state[0].size, self._state[0].dtype, grad.size, grad.dtype))
+
     def _run(self, param, step_out, grad):
         if self.opt_code is None:
             raise NotImplementedError

@@ -273,6 +273,12 @@ int tnn_nccl_init(int rank, int world, const void* id128);
 int tnn_nccl_destroy(void);
 int tnn_allreduce_sum(int dtype, void* buf, int64_t n);    /* in place, compute stream */
 int tnn_allgather(int dtype, void* recv, const void* send, int64_t n_per_rank);
+/* chunked all-reduce on a second (comm) stream, so the optimiser kernel of chunk i runs while chunk
+ * i+1 is on the wire: tnn_comm_wait_compute(); { tnn_allreduce_sum_comm(chunk); tnn_compute_wait_comm();
+ * tnn_opt_step(chunk) } per chunk */
+int tnn_comm_wait_compute(void);          /* comm stream waits for work queued so far on compute   */
+int tnn_compute_wait_comm(void);          /* compute stream waits for collectives queued so far    */
+int tnn_allreduce_sum_comm(int dtype, void* buf, int64_t n);   /* in place, comm stream           */
 int tnn_nccl_version(int* v);
 
 #ifdef __cplusplus

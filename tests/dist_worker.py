@@ -83,6 +83,30 @@ def main():
             assert np.array_equal(pe[k].values, pg[k].values)
     if rank == 0:
         print("GRAPH_DIST_OK world=%d" % world)
+
+    # chunked all-reduce pipelined with the optimiser kernel (what the wide MLP uses): force it on
+    # this small model; with two ranks a SUM is order-independent, so it must match bit for bit
+    from core.optimizer import Adam
+    results = []
+    for min_elems, n_chunks in ((1 << 20, 1), (64, 4)):
+        dist.MIN_CHUNK_ELEMS, dist.ALLREDUCE_CHUNKS = min_elems, n_chunks
+        np.random.seed(2)
+        n = Net([Dense(24, num_in=D), ReLU(), Dense(C, num_in=24)])
+        m = Model(net=n, loss=SoftmaxCrossEntropyLoss(), optimizer=Adam(lr=1e-2))
+        ls = []
+        for _ in range(5):
+            m.zero_grad()
+            loss = m.loss.loss(m.forward(xs), ys)
+            loss.backward()
+            m.step()
+            ls.append(float(loss.values))
+        results.append((ls, [p.values.copy() for layer in n.get_parameters() for p in layer.values()]))
+    dist.MIN_CHUNK_ELEMS, dist.ALLREDUCE_CHUNKS = 1 << 20, 1
+    assert results[0][0] == results[1][0], (results[0][0], results[1][0])
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.array_equal(a, b)
+    if rank == 0:
+        print("CHUNKED_DIST_OK world=%d" % world)
     dist.barrier()
     dist.destroy_process_group()
 

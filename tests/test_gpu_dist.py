@@ -34,3 +34,4 @@ def test_two_rank_training_equals_full_batch_oracle():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_OK world=2" in r.stdout
     assert "GRAPH_DIST_OK world=2" in r.stdout
+    assert "CHUNKED_DIST_OK world=2" in r.stdout

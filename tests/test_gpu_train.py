@@ -327,3 +327,31 @@ def test_prefetch_iterator_delivers_the_right_rows():
     sizes = [len(next(feed).inputs) for _ in range(7)]
     assert sizes == [400, 400, 200, 400, 400, 200, 400]
     feed.close()
+
+
+def test_predict_builds_no_graph_and_matches_forward():
+    """Model.predict / ops.no_grad: same values as forward(), no autograd graph, training unaffected"""
+    import core.ops as ops
+    from core.tensor import Tensor
+    rng = np.random.RandomState(2)
+    x = rng.rand(64, 48).astype(np.float32)
+    labels = np.eye(10)[rng.randint(0, 10, 64)]
+    np.random.seed(4)
+    net, model, loss_layer = _build([32, 16, 10])
+    ref = model.forward(Tensor(x))
+    out = model.predict(x)
+    assert np.array_equal(out.values, ref.values)
+    assert ref.requires_grad and len(ref.dependency) > 0
+    assert not out.requires_grad and out.dependency == []
+    with pytest.raises(AssertionError):
+        out.backward()
+    with ops.no_grad():
+        t = Tensor(x, requires_grad=True) * 2.0 + 1.0
+    assert not t.requires_grad
+    assert np.argmax(out, axis=1).shape == (64,)          # run.py:89 consumes a Tensor through __array__
+    # the graph machinery is back on afterwards
+    model.zero_grad()
+    loss = loss_layer.loss(model.forward(Tensor(x)), Tensor(labels))
+    loss.backward()
+    model.step()
+    assert np.isfinite(float(loss.values))

@@ -107,6 +107,7 @@ int tnn_nccl_init(int rank, int world, const void* id128) {
 int tnn_nccl_destroy(void) {
   if (g_comm) {
     cudaStreamSynchronize(ctx().stream);
+    cudaStreamSynchronize(ctx().comm_stream);
     g_api.CommDestroy(g_comm);
     g_comm = nullptr;
   }
@@ -121,6 +122,39 @@ int tnn_allreduce_sum(int dtype, void* buf, int64_t n) {
   if (dtype != TNN_F32 && dtype != TNN_F64) TNN_FAIL("tnn_allreduce_sum: bad dtype");
   TNN_NCCL(g_api.AllReduce(buf, buf, (size_t)n, dtype == TNN_F32 ? ncclFloat32 : ncclFloat64, ncclSum,
                            g_comm, ctx().stream));
+  ctx().launches++;
+  return 0;
+}
+
+// ---- all-reduce beside the optimiser -------------------------------------------------------------
+// The gradient arena is reduced in chunks on a second stream; the fused optimiser kernel for chunk
+// i runs on the compute stream as soon as chunk i is reduced, while chunk i+1 is still on the wire:
+//     tnn_comm_wait_compute();                       backward has produced every gradient
+//     for each chunk: tnn_allreduce_sum_comm(chunk); tnn_compute_wait_comm(); optimiser(chunk)
+// (Overlap with the backward GEMMs themselves is not possible today: the persistent GEMM owns every
+// SM's register file)
+int tnn_comm_wait_compute(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  TNN_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+  TNN_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_compute, 0));
+  return 0;
+}
+
+int tnn_compute_wait_comm(void) {
+  TNN_REQUIRE_INIT();
+  Context& c = ctx();
+  TNN_CUDA(cudaEventRecord(c.ev_comm, c.comm_stream));
+  TNN_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
+  return 0;
+}
+
+int tnn_allreduce_sum_comm(int dtype, void* buf, int64_t n) {
+  TNN_REQUIRE_INIT();
+  if (!g_comm) TNN_FAIL("tnn_allreduce_sum_comm: call tnn_nccl_init first");
+  if (dtype != TNN_F32 && dtype != TNN_F64) TNN_FAIL("tnn_allreduce_sum_comm: bad dtype");
+  TNN_NCCL(g_api.AllReduce(buf, buf, (size_t)n, dtype == TNN_F32 ? ncclFloat32 : ncclFloat64, ncclSum,
+                           g_comm, ctx().comm_stream));
   ctx().launches++;
   return 0;
 }

@@ -16,6 +16,8 @@ struct Context {
   size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;       // compute stream: every kernel goes here
   cudaStream_t copy_stream = nullptr;  // H2D prefetch
+  cudaStream_t comm_stream = nullptr;  // gradient all-reduce chunks running beside the optimiser (comm.cu)
+  cudaEvent_t ev_comm = nullptr;       // last comm-stream fence
   cudaEvent_t ev_copy = nullptr;       // last copy-stream fence
   cudaEvent_t ev_compute = nullptr;    // last compute-stream fence
   uint64_t launches = 0;               // kernels launched by this library

@@ -163,6 +163,8 @@ int tnn_init(int device) {
   c.l2_bytes = (size_t)prop.l2CacheSize;
   TNN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   TNN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  TNN_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  TNN_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
   TNN_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
   TNN_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
   c.inited = true;
@@ -174,6 +176,7 @@ int tnn_shutdown(void) {
   if (!c.inited) return 0;
   cudaStreamSynchronize(c.stream);
   cudaStreamSynchronize(c.copy_stream);
+  cudaStreamSynchronize(c.comm_stream);
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     for (auto& kv : g_pool.owned) cudaFree(kv.first);
@@ -193,6 +196,8 @@ int tnn_shutdown(void) {
   cudaEventDestroy(c.ev_compute);
   cudaStreamDestroy(c.stream);
   cudaStreamDestroy(c.copy_stream);
+  cudaEventDestroy(c.ev_comm);
+  cudaStreamDestroy(c.comm_stream);
   c.inited = false;
   return 0;
 }
