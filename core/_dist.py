@@ -94,6 +94,13 @@ ALLREDUCE_CHUNKS = int(os.environ.get("TNN_ALLREDUCE_CHUNKS", "1"))
 MIN_CHUNK_ELEMS = 1 << 20     # pieces below this are not worth a launch of their own
 
 
+def chunk_bounds(n, chunks, align):
+    """[(lo, hi)] covering [0, n) in at most `chunks` pieces whose starts are multiples of `align`"""
+    per = -(-n // chunks)
+    per = (per + align - 1) // align * align
+    return [(lo, min(lo + per, n)) for lo in range(0, n, per)]
+
+
 def reduce_and_apply(optimizer, param_flat, grad_flat, align=64):
     """SUM all-reduce of the flat gradient arena pipelined with the fused optimiser: the arena is
     cut into ALLREDUCE_CHUNKS pieces, piece i+1 is reduced on the comm stream while the optimiser
@@ -105,9 +112,7 @@ def reduce_and_apply(optimizer, param_flat, grad_flat, align=64):
         allreduce_sum(grad_flat)
         optimizer.apply_fused(param_flat, grad_flat)
         return
-    per = -(-n // chunks)
-    per = (per + align - 1) // align * align
-    bounds = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
+    bounds = chunk_bounds(n, chunks, align)
     if be._lib.tnn_comm_wait_compute():
         be._raise("tnn_comm_wait_compute")
     code = be._DT_CODE[grad_flat.dtype]

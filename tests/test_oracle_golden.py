@@ -189,3 +189,28 @@ def test_mlp_step_matches_reference(golden_dir):
     assert np.max(np.abs(np.array(losses) - gold["losses"])) <= 1e-9
     for k, p in enumerate(mlp.params()):
         assert op_cases.rel_err(p.values, gold["param%d" % k]) <= 1e-10
+
+
+def test_operand_split_error_model():
+    """the error of the tensor-core operand splits with exact accumulation: the
+    mixed TF32 + 2xBF16 split stays below 1e-6 of max|A@B|, 3xTF32 below 1.5e-7, a single TF32 pass
+    is three orders of magnitude worse"""
+    import split_error_model as S
+    rng = np.random.RandomState(0)
+    for gen, K in ((lambda s: rng.standard_normal(s), 4096), (lambda s: rng.rand(*s), 4096),
+                   (lambda s: rng.rand(*s) - 0.3, 1024), (lambda s: rng.standard_normal(s), 128)):
+        a, b = gen((192, K)).astype(np.float32), gen((K, 160)).astype(np.float32)
+        exact = a.astype(np.float64) @ b.astype(np.float64)
+        e3 = S.rel_err(S.product_tf32x3(a, b), exact)
+        em = S.rel_err(S.product_mix(a, b), exact)
+        e1 = S.rel_err(S.product_single_tf32(a, b), exact)
+        assert e3 <= 1.5e-7 and em <= 1e-6 and e1 >= 20 * em, (e3, em, e1)
+
+
+def test_allreduce_chunk_bounds():
+    import core._dist as dist
+    for n, chunks, align in ((67125248, 4, 64), (1000, 4, 64), (64, 4, 64), (130, 2, 64), (1 << 20, 8, 64)):
+        b = dist.chunk_bounds(n, chunks, align)
+        assert b[0][0] == 0 and b[-1][1] == n and len(b) <= chunks
+        assert all(lo % align == 0 for lo, _ in b)
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
