@@ -24,7 +24,7 @@ for s in $STAGES; do
     bench_n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/bench_n4.log 2>&1 ;;
     bench_n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/bench_n8.log 2>&1 ;;
     bench1) timeout 900 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1 ;;
-    memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_autograd_cases.py tests/test_gpu_gemm.py -m gpu -q -x -p no:cacheprovider > gpurun_out/memcheck.log 2>&1 ;;
+    memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_autograd_cases.py tests/test_gpu_gemm.py tests/test_gpu_graph.py tests/test_gpu_train.py -m gpu -q -x -p no:cacheprovider > gpurun_out/memcheck.log 2>&1 ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1,-8,-4,-2,1,-8,-4,-2 > gpurun_out/gemm_bench.jsonl 2>&1 ;;
     ab_fuse) for i in 1 2 3; do TNN_FUSE_RELU=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse1.log 2>&1; TNN_FUSE_RELU=0 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline >> gpurun_out/ab_fuse0.log 2>&1; done ;;
     ncu_mnist) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv --log-file gpurun_out/launches_mnist.csv python bench.py --workload mnist --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/ncu_mnist.log 2>&1 ;;
