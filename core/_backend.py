@@ -6,6 +6,7 @@ raises.  The reference's numpy calls in core/ops.py map onto the functions here 
 (citations in include/tnn_b200.h).
 """
 import ctypes
+import gc
 import os
 import weakref
 
@@ -93,6 +94,8 @@ _SIGNATURES = {
     "tnn_scatter_flat": [_c_int, _c_vp, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_simt": [_c_int, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64,
                       _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_vp],
+    "tnn_dense_bwd_simt": [_c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int,
+                           _c_i64, _c_i64, _c_i64],
     "tnn_split_tf32": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64],
     "tnn_gemm_tf32x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64,
                         _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -798,6 +801,32 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
     return (out, act_out) if act else out
 
 
+GROUPED_BWD_MAX_TILES = 1024   # above this the three products are big enough to launch on their own
+
+
+def dense_bwd_grouped_ok(B, K, N, dtype):
+    """small Dense layer: its three gradient products go out as one grouped SIMT launch"""
+    if use_tensor_cores(B, K, N, dtype) or use_tensor_cores(K, N, B, dtype):
+        return False
+    t = lambda m, n: ((m + 31) // 32) * ((n + 31) // 32)
+    return t(K, N) + t(B, K) + t(1, N) <= GROUPED_BWD_MAX_TILES
+
+
+def dense_bwd_grouped(g, x, w, mask_src, need_dx, dw_out, dw_acc, db_out, db_acc):
+    """(dx, dx_masked) -- either may be None -- with dW / db written (or accumulated) in place"""
+    B, N = g.shape
+    K = w.shape[0]
+    dx = empty((B, K), g.dtype) if need_dx else None
+    masked = empty((B, K), g.dtype) if (need_dx and mask_src is not None) else None
+    if _lib.tnn_dense_bwd_simt(_DT_CODE[g.dtype], g.ptr, x.ptr, w.ptr,
+                               mask_src.ptr if masked is not None else None,
+                               dx.ptr if dx is not None else None,
+                               masked.ptr if masked is not None else None,
+                               dw_out.ptr, 1 if dw_acc else 0, db_out.ptr, 1 if db_acc else 0, B, K, N):
+        _raise("tnn_dense_bwd_simt")
+    return dx, masked
+
+
 # --------------------------------------------------------------------------------------------
 # fused layer / loss / optimizer kernels
 # --------------------------------------------------------------------------------------------
@@ -1044,19 +1073,30 @@ class _Capture(object):
     def __enter__(self):
         if self.graph.handle:
             raise BackendError("StepGraph already holds a captured step")
+        # the cyclic garbage collector must not run finalisers (which may synchronise the stream or
+        # free pinned memory) in the middle of a capture: collect now, pause it until the end
+        gc.collect()
+        self._gc_was_enabled = gc.isenabled()
+        gc.disable()
         if _lib.tnn_graph_begin():
+            if self._gc_was_enabled:
+                gc.enable()
             _raise("tnn_graph_begin")
         return self.graph
 
     def __exit__(self, exc_type, exc, tb):
-        if exc_type is not None:
-            _lib.tnn_graph_abort()
+        try:
+            if exc_type is not None:
+                _lib.tnn_graph_abort()
+                return False
+            h = _c_vp()
+            if _lib.tnn_graph_end(ctypes.byref(h)):
+                _raise("tnn_graph_end")
+            self.graph.handle = h.value
             return False
-        h = _c_vp()
-        if _lib.tnn_graph_end(ctypes.byref(h)):
-            _raise("tnn_graph_end")
-        self.graph.handle = h.value
-        return False
+        finally:
+            if self._gc_was_enabled:
+                gc.enable()
 
 
 def prof_enable(family):

@@ -22,6 +22,9 @@ import core._backend as be
 # there it is opt-in.  On the SIMT path (MNIST-sized layers, launch-bound) it is always on: one
 # launch less per hidden layer.
 FUSE_RELU_BWD = os.environ.get("TNN_FUSE_RELU_BWD", "0") != "0"
+# dX, dW and db of a small Dense layer as one grouped launch (tnn_dense_bwd_simt)
+GROUP_SMALL_DENSE_BWD = os.environ.get("TNN_GROUP_DENSE_BWD", "1") != "0"
+WRITTEN_IN_PLACE = object()   # returned by a node's _fused_bwd for gradients it wrote into their slot
 
 
 _GRAD_ENABLED = True
@@ -523,13 +526,38 @@ def _dense_node(ts_x, ts_w, ts_b, values):
         s = be.colsum(grad)
         return be.add_inplace(out, s) if out is not None else s
 
+    def fused_bwd(grad, direct):
+        """All three gradients from ONE grouped launch when the layer is small (MNIST-sized: a launch
+        costs more than the arithmetic).  `direct` maps id(tensor) -> (arena slot, accumulate) for the
+        leaves the kernel may write in place; returns {id(tensor): gradient or WRITTEN_IN_PLACE}, or
+        None when this node should go through the per-input functions instead."""
+        b = ts_b._data
+        if not (ts_w.requires_grad and ts_b.requires_grad and id(ts_w) in direct and id(ts_b) in direct):
+            return None
+        if ts_w is ts_b or not (grad.dtype == x.dtype == w.dtype == b.dtype) or grad.ndim != 2:
+            return None
+        if not be.dense_bwd_grouped_ok(grad.shape[0], w.shape[0], w.shape[1], grad.dtype):
+            return None
+        mask = pre if (pre is not None and pre.dtype == grad.dtype) else None
+        (w_slot, w_acc), (b_slot, b_acc) = direct[id(ts_w)], direct[id(ts_b)]
+        dx, masked = be.dense_bwd_grouped(grad, x, w, mask, ts_x.requires_grad, w_slot, w_acc, b_slot, b_acc)
+        out = {id(ts_w): WRITTEN_IN_PLACE, id(ts_b): WRITTEN_IN_PLACE}
+        if ts_x.requires_grad:
+            if masked is not None:
+                dx.aux = (pre, masked)
+            out[id(ts_x)] = dx
+        return out
+
     grad_fn_x.supports_out = grad_fn_w.supports_out = grad_fn_b.supports_out = True
     dependency = []
     requires_grad = (ts_x.requires_grad or ts_w.requires_grad or ts_b.requires_grad) and _GRAD_ENABLED
     for t, fn in ((ts_x, grad_fn_x), (ts_w, grad_fn_w), (ts_b, grad_fn_b)):
         if t.requires_grad and requires_grad:
             dependency.append(dict(tensor=t, grad_fn=fn))
-    return ts_x.__class__(values, requires_grad, dependency)
+    node = ts_x.__class__(values, requires_grad, dependency)
+    if requires_grad and GROUP_SMALL_DENSE_BWD and ts_x is not ts_w and ts_x is not ts_b:
+        node._fused_bwd = fused_bwd
+    return node
 
 
 def dense_relu_(ts_x, ts_w, ts_b):

@@ -48,6 +48,7 @@ class Tensor(object):
         self._grad_host = None
         self._gslot = None       # view into a flat gradient arena (set by core.model.Model)
         self._relu_pre = None    # pre-activation array when this tensor is a fused ReLU output
+        self._fused_bwd = None   # optional: all input gradients of this node from one launch (ops._dense_node)
         self.requires_grad = requires_grad
         if self.requires_grad:
             self.zero_grad()
@@ -289,6 +290,33 @@ class Tensor(object):
             self._grad = be.ew(be.ADD, self._grad, g)
         self._grad_zero = False
 
+    @staticmethod
+    def _run_fused_bwd(node, g, pending):
+        """let a node produce all its input gradients at once; False = use the per-input functions"""
+        direct = {}
+        for dep in node.dependency:
+            t = dep["tensor"]
+            if (t._gslot is not None and t._grad is t._gslot and not t.dependency
+                    and id(t) not in pending):
+                direct[id(t)] = (t._gslot, not t._grad_zero)
+        results = node._fused_bwd(g, direct)
+        if results is None:
+            return False
+        for dep in node.dependency:
+            t = dep["tensor"]
+            r = results[id(t)]
+            if r is ops.WRITTEN_IN_PLACE:
+                t._grad_zero = False
+                t._grad_host = None
+                continue
+            gd = t._coerce_grad(r)
+            key = id(t)
+            if key in pending:
+                pending[key] = be.ew(be.ADD, pending[key], gd)
+            else:
+                pending[key] = gd
+        return True
+
     def backward(self, grad=None):
         assert self.requires_grad, "Call backward() on a non-requires-grad tensor."
         if grad is None:
@@ -321,6 +349,8 @@ class Tensor(object):
             if g is None:
                 continue
             node._accumulate(g)
+            if node._fused_bwd is not None and self._run_fused_bwd(node, g, pending):
+                continue
             for dep in node.dependency:
                 t = dep["tensor"]
                 fn = dep["grad_fn"]

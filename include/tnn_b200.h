@@ -178,6 +178,15 @@ int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev
 int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs, int64_t a_cs,
                   const void* B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
                   const void* bias, int flags, void* act_out, const void* mask_src);
+/* The three gradient products of a SMALL Dense layer (ops.py:156-160 and the bias un-broadcast
+ * ops.py:49-55) in one grouped SIMT launch: dx[B,K] = g[B,N] @ w[K,N]^T (dx may be NULL: the first
+ * layer's input needs no gradient), dx_masked[B,K] = dx * (mask_src >= 0) (may be NULL; the ReLU
+ * backward of the layer below), dw[K,N] (+)= x[B,K]^T @ g, db[1,N] (+)= column sums of g.  All
+ * arrays contiguous row-major.  Meant for layers whose products are a handful of 32x32 tiles (the
+ * examples/mnist MLP), where a launch costs more than the arithmetic. */
+int tnn_dense_bwd_simt(int dtype, const void* g, const void* x, const void* w, const void* mask_src,
+                       void* dx, void* dx_masked, void* dw, int dw_accumulate, void* db,
+                       int db_accumulate, int64_t B, int64_t K, int64_t N);
 /* fp32 -> (hi, lo) tf32 planes for the 3xTF32 tensor-core GEMM.  x is [R, C] row-major (ld = C).
  * plain planes  hi/lo  : [R, ldp]  (ldp >= C, multiple of 4)   -- may be NULL
  * transposed    hiT/loT: [C, ldt]  (ldt >= R, multiple of 4)   -- may be NULL */

@@ -71,7 +71,7 @@ def test_captured_mnist_step_is_bit_identical(opt):
     states = [s for s in model_b._captured.values()]
     assert len(states) == 2 and all(hasattr(s, "graph") for s in states)   # both shapes were recorded
     info = states[0].info()
-    assert info["kernel_nodes"] >= 20 and info["blocks"] > 0
+    assert info["kernel_nodes"] >= 10 and info["blocks"] > 0
     for pa, pb in zip(_params(net_a), _params(net_b)):
         assert np.array_equal(pa, pb)
 
@@ -148,3 +148,24 @@ def test_host_transfer_inside_capture_fails_loudly():
     # the aborted capture left the stream usable
     a = be.from_numpy(np.arange(4, dtype=np.float32))
     assert np.array_equal(be.to_numpy(be.ew(be.ADD, a, a)), 2 * np.arange(4, dtype=np.float32))
+
+
+def test_graph_destroyed_during_another_capture_is_deferred():
+    """a recorded step released while a second capture is running (the garbage collector can do
+    that) must not synchronise the stream: its destruction waits for the capture to end"""
+    import core._backend as be
+    a = be.from_numpy(np.arange(8, dtype=np.float32))
+    g1 = be.StepGraph()
+    with g1.capture():
+        b = be.ew(be.ADD, a, a)
+    g1.replay()
+    assert np.array_equal(be.to_numpy(b), 2 * np.arange(8, dtype=np.float32))
+    g2 = be.StepGraph()
+    with g2.capture():
+        c = be.ew(be.MUL, a, a)
+        g1.destroy()                       # in the middle of g2's capture
+        d = be.ew(be.ADD, c, a)
+    g2.replay()
+    x = np.arange(8, dtype=np.float32)
+    assert np.array_equal(be.to_numpy(d), x * x + x)
+    g2.destroy()

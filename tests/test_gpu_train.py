@@ -355,3 +355,66 @@ def test_predict_builds_no_graph_and_matches_forward():
     loss.backward()
     model.step()
     assert np.isfinite(float(loss.values))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_grouped_dense_backward_matches_separate_launches(dtype):
+    """small Dense layers: dX / dW / db from one grouped launch (tnn_dense_bwd_simt) against the
+    three separate products, through the whole MLP backward, including a second backward() that
+    accumulates into the arena slots"""
+    import core.initializer as I
+    import core.ops as ops
+    from core.layers import Dense, ReLU
+    from core.losses import SoftmaxCrossEntropyLoss
+    from core.model import Model
+    from core.nn import Net
+    from core.optimizer import SGD
+    from core.tensor import Tensor
+
+    class Xavier(I.XavierUniformInit):
+        def __call__(self, shape):
+            return Tensor(self.init(shape).astype(np.float32), requires_grad=True, dtype=dtype)
+
+    class Zeros(I.ZerosInit):
+        def __call__(self, shape):
+            return Tensor(self.init(shape), requires_grad=True, dtype=dtype)
+
+    rng = np.random.RandomState(3)
+    x = rng.rand(80, 50).astype(dtype)
+    labels = np.eye(10)[rng.randint(0, 10, 80)]
+    tol = 2e-6 if dtype == np.float32 else 1e-12
+    old = ops.GROUP_SMALL_DENSE_BWD
+    out = {}
+    try:
+        for grouped in (True, False):
+            ops.GROUP_SMALL_DENSE_BWD = grouped
+            np.random.seed(5)
+            widths = [70, 33, 10]
+            layers = []
+            for i, wd in enumerate(widths):
+                layers.append(Dense(wd, w_init=Xavier(), b_init=Zeros()))
+                if i + 1 < len(widths):
+                    layers.append(ReLU())
+            net = Net(layers)
+            model = Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=SGD(lr=0.1))
+            xin = Tensor(x, requires_grad=True)
+            # step 1 builds the arenas; afterwards gradients are written straight into their slots
+            model.zero_grad()
+            model.loss.loss(model.forward(Tensor(x)), Tensor(labels)).backward()
+            model.step()
+            model.zero_grad()
+            loss = model.loss.loss(model.forward(xin), Tensor(labels))
+            loss.backward()
+            first = [p.grad.copy() for layer in net.get_parameters() for p in layer.values()]
+            loss2 = model.loss.loss(model.forward(xin), Tensor(labels))
+            loss2.backward()                      # accumulates on top
+            second = [p.grad.copy() for layer in net.get_parameters() for p in layer.values()]
+            out[grouped] = (first, second, xin.grad.copy(), layers[1].inputs.grad.copy())
+    finally:
+        ops.GROUP_SMALL_DENSE_BWD = old
+    for a, b in zip(out[True][0] + out[True][1], out[False][0] + out[False][1]):
+        assert op_cases.rel_err(a, b) <= tol
+    assert op_cases.rel_err(out[True][2], out[False][2]) <= tol      # dL/dx of the input batch
+    assert op_cases.rel_err(out[True][3], out[False][3]) <= tol      # non-leaf .grad of a pre-activation
+    for a, b in zip(out[True][0], out[True][1]):
+        assert op_cases.rel_err(b, 2 * a) <= 10 * tol                # second backward doubled it

@@ -21,23 +21,22 @@ namespace cg = cooperative_groups;
 
 namespace tnn {
 
-// SPLITK: gridDim.z CTAs (one cluster) share an output tile, CTA z covers k in [z*kslice, ...)
+// One output tile.  SPLITK: gridDim.z CTAs (one cluster) share the tile, CTA z covers k in
+// [z*kslice, ...).  A == nullptr stands for a matrix of ones (the bias gradient 1^T g as a product).
 template <typename T, int BM, int BN, int BK, int TM, int TN, bool SPLITK>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN), BM == 32 ? 2 : 1)   // small tiles: two CTAs per SM, so an 8-way K cluster of 28 tiles is one wave
-gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_t a_rs, int64_t a_cs,
-                 const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
-                 const T* __restrict__ bias, int flags, T* __restrict__ act_out,
-                 const T* __restrict__ mask_src, int64_t kslice) {
+__device__ __forceinline__ void
+gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restrict__ C, int64_t ldc,
+          const T* __restrict__ A, int64_t a_rs, int64_t a_cs, const T* __restrict__ B, int64_t b_rs,
+          int64_t b_cs, int64_t M, int64_t N, int64_t K, const T* __restrict__ bias, int flags,
+          T* __restrict__ act_out, const T* __restrict__ mask_src, int64_t kslice) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_PER = (BM * BK) / NT;
   constexpr int B_PER = (BK * BN) / NT;
   static_assert((BM * BK) % NT == 0 && (BK * BN) % NT == 0, "tile/threads mismatch");
-  __shared__ T As[BK][BM + 1];
-  __shared__ T Bs[BK][BN + 1];
 
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
-  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t m0 = (int64_t)tile_y * BM, n0 = (int64_t)tile_x * BN;
   const bool a_kfast = (a_cs == 1);   // k contiguous in memory
   const bool b_nfast = (b_cs == 1);   // n contiguous in memory
 
@@ -56,7 +55,7 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
       int m = a_kfast ? idx / BK : idx % BM;
       int k = a_kfast ? idx % BK : idx / BM;
       int64_t gm = m0 + m, gk = k0 + k;
-      ra[e] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : T(0);
+      ra[e] = (gm < M && gk < K) ? (A ? A[gm * a_rs + gk * a_cs] : T(1)) : T(0);
     }
 #pragma unroll
     for (int e = 0; e < B_PER; ++e) {
@@ -174,6 +173,58 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
   }
 }
 
+template <typename T, int BM, int BN, int BK, int TM, int TN, bool SPLITK>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), BM == 32 ? 2 : 1)   // small tiles: two CTAs per SM, so an 8-way K cluster of 28 tiles is one wave
+gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_t a_rs, int64_t a_cs,
+                 const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
+                 const T* __restrict__ bias, int flags, T* __restrict__ act_out,
+                 const T* __restrict__ mask_src, int64_t kslice) {
+  __shared__ T As[BK][BM + 1];
+  __shared__ T Bs[BK][BN + 1];
+  gemm_tile<T, BM, BN, BK, TM, TN, SPLITK>(As, Bs, (int)blockIdx.x, (int)blockIdx.y, C, ldc, A, a_rs, a_cs,
+                                           B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, kslice);
+}
+
+// ---- grouped launch: the three gradient products of a small Dense layer in one kernel -------------
+// dX = g @ w^T (+ the ReLU mask of the layer below), dW = x^T @ g, db = 1^T @ g are independent given
+// g; for the MNIST-sized layers each is a handful of 32x32 tiles and a launch costs more than the
+// arithmetic, so they share one grid: CTA b works on tile (b - first[p]) of problem p.
+template <typename T>
+struct SimtProblem {
+  T* C;
+  int64_t ldc;
+  const T* A;
+  int64_t a_rs, a_cs;
+  const T* B;
+  int64_t b_rs, b_cs;
+  int64_t M, N, K;
+  int flags;
+  T* act_out;
+  const T* mask_src;
+  int tiles_x, first;     // tiles per row of this problem's tile grid, first CTA index
+};
+template <typename T>
+struct SimtGroup {
+  SimtProblem<T> p[3];
+  int count;
+};
+
+template <typename T, int BK>
+__global__ void __launch_bounds__(256, 2)
+gemm_simt_group_kernel(const SimtGroup<T> grp) {
+  __shared__ T As[BK][33];
+  __shared__ T Bs[BK][33];
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 3; ++i)
+    if (i < grp.count && (int)blockIdx.x >= grp.p[i].first) pi = i;
+  const SimtProblem<T>& q = grp.p[pi];
+  const int local = (int)blockIdx.x - q.first;
+  gemm_tile<T, 32, 32, BK, 2, 2, false>(As, Bs, local % q.tiles_x, local / q.tiles_x, q.C, q.ldc, q.A, q.a_rs,
+                                        q.a_cs, q.B, q.b_rs, q.b_cs, q.M, q.N, q.K, nullptr, q.flags,
+                                        q.act_out, q.mask_src, 0);
+}
+
 template <typename T>
 static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
                           int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
@@ -227,9 +278,59 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
   return 0;
 }
 
+// dX[B,K] = g[B,N] @ w[K,N]^T (optional; with mask: masked = dX * (mask >= 0)),
+// dW[K,N] (+)= x[B,K]^T @ g[B,N],  db[1,N] (+)= column sums of g -- one grouped launch
+template <typename T>
+static int dense_bwd_impl(const T* g, const T* x, const T* w, const T* mask, T* dx, T* masked, T* dw,
+                          int dw_acc, T* db, int db_acc, int64_t Bn, int64_t K, int64_t N) {
+  SimtGroup<T> grp;
+  grp.count = 0;
+  int next = 0;
+  auto add = [&](T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a_cs, const T* Bm, int64_t b_rs,
+                 int64_t b_cs, int64_t M, int64_t Nn, int64_t Kk, int flags, T* act, const T* msk) {
+    SimtProblem<T>& q = grp.p[grp.count++];
+    q.C = C; q.ldc = ldc; q.A = A; q.a_rs = a_rs; q.a_cs = a_cs; q.B = Bm; q.b_rs = b_rs; q.b_cs = b_cs;
+    q.M = M; q.N = Nn; q.K = Kk; q.flags = flags; q.act_out = act; q.mask_src = msk;
+    q.tiles_x = (int)ceil_div(Nn, 32);
+    q.first = next;
+    next += q.tiles_x * (int)ceil_div(M, 32);
+  };
+  // the deepest products first: their CTAs start first and finish last
+  add(dw, N, x, 1, K, g, N, 1, K, N, Bn, dw_acc ? 1 : 0, nullptr, nullptr);          // x^T @ g
+  if (dx) add(dx, K, g, N, 1, w, 1, N, Bn, K, N, 0, masked, masked ? mask : nullptr);   // g @ w^T
+  add(db, N, nullptr, 0, 0, g, N, 1, 1, N, Bn, db_acc ? 1 : 0, nullptr, nullptr);      // 1^T @ g
+  constexpr int SBK = sizeof(T) == 4 ? 128 : 64;
+  prof_begin(2);
+  gemm_simt_group_kernel<T, SBK><<<next, 256, 0, ctx().stream>>>(grp);
+  TNN_POST_LAUNCH();
+  prof_end(2);
+  return 0;
+}
+
 }  // namespace tnn
 
 using namespace tnn;
+
+extern "C" int tnn_dense_bwd_simt(int dtype, const void* g, const void* x, const void* w,
+                                  const void* mask_src, void* dx, void* dx_masked, void* dw,
+                                  int dw_accumulate, void* db, int db_accumulate, int64_t B, int64_t K,
+                                  int64_t N) {
+  TNN_REQUIRE_INIT();
+  if (B <= 0 || K <= 0 || N <= 0) TNN_FAIL("tnn_dense_bwd_simt: empty operand");
+  if (!g || !x || !w || !dw || !db) TNN_FAIL("tnn_dense_bwd_simt: g, x, w, dw, db are required");
+  if (dx_masked && (!dx || !mask_src)) TNN_FAIL("tnn_dense_bwd_simt: dx_masked needs dx and mask_src");
+  if (ceil_div(K, 32) * ceil_div(N, 32) + ceil_div(B, 32) * ceil_div(K, 32) + ceil_div(N, 32) > 65535)
+    TNN_FAIL("tnn_dense_bwd_simt: layer too large for the grouped SIMT launch");
+  if (dtype == TNN_F32)
+    return dense_bwd_impl<float>((const float*)g, (const float*)x, (const float*)w, (const float*)mask_src,
+                                 (float*)dx, (float*)dx_masked, (float*)dw, dw_accumulate, (float*)db,
+                                 db_accumulate, B, K, N);
+  if (dtype == TNN_F64)
+    return dense_bwd_impl<double>((const double*)g, (const double*)x, (const double*)w,
+                                  (const double*)mask_src, (double*)dx, (double*)dx_masked, (double*)dw,
+                                  dw_accumulate, (double*)db, db_accumulate, B, K, N);
+  TNN_FAIL("tnn_dense_bwd_simt: dtype must be TNN_F32 or TNN_F64");
+}
 
 extern "C" int tnn_gemm_simt(int dtype, void* C, int64_t ldc, const void* A, int64_t a_rs,
                              int64_t a_cs, const void* B, int64_t b_rs, int64_t b_cs, int64_t M,

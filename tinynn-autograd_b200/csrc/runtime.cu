@@ -62,6 +62,7 @@ static std::unordered_map<void*, Graph*> g_block_graph;         // block -> owni
 static int g_graph_ids = 0;
 static int g_live_graphs = 0;
 static std::vector<void*> g_retired_scratch;                    // old scratch a live graph may still name
+static std::vector<Graph*> g_deferred_destroy;                  // destroyed while another capture was running
 
 static size_t round_size(size_t n) {
   if (n == 0) n = 1;
@@ -204,6 +205,7 @@ int tnn_shutdown(void) {
 
 int tnn_sync(void) {
   TNN_REQUIRE_INIT();
+  if (g_capture) TNN_FAIL("tnn_sync: a graph capture is in progress (nothing is running yet)");
   TNN_CUDA(cudaStreamSynchronize(ctx().stream));
   return 0;
 }
@@ -320,6 +322,7 @@ int tnn_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* n_cuda_
 
 int tnn_pool_trim(void) {
   TNN_REQUIRE_INIT();
+  if (g_capture) TNN_FAIL("tnn_pool_trim: a graph capture is in progress");
   TNN_CUDA(cudaStreamSynchronize(ctx().stream));
   std::lock_guard<std::mutex> lk(g_pool.mu);
   pool_release_all_free_locked();
@@ -463,6 +466,8 @@ int tnn_prof_collect(double* total_ms, uint64_t* n_launches) {
   return 0;
 }
 
+static void drain_deferred_destroys();
+
 // ---- captured steps (CUDA graphs) --------------------------------------------------------------
 // The MNIST-shaped training step is ~35 launches of a few microseconds each: issued one by one
 // from Python it is bound by launch overhead.  tnn_graph_begin/end record everything the host
@@ -516,6 +521,7 @@ int tnn_graph_end(void** graph_out) {
       graph_release_blocks_locked(g);
     }
     delete g;
+    drain_deferred_destroys();
     TNN_FAIL(std::string("graph capture failed: ") + cudaGetErrorString(e));
   }
   size_t n = 0;
@@ -531,6 +537,7 @@ int tnn_graph_end(void** graph_out) {
   }
   g_live_graphs++;
   *graph_out = (void*)g;
+  drain_deferred_destroys();
   return 0;
 }
 
@@ -542,10 +549,13 @@ int tnn_graph_abort(void) {
   cudaStreamEndCapture(ctx().stream, &tmp);
   cudaGetLastError();
   if (tmp) cudaGraphDestroy(tmp);
-  std::lock_guard<std::mutex> lk(g_pool.mu);
-  g_capture = nullptr;
-  graph_release_blocks_locked(g);
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_capture = nullptr;
+    graph_release_blocks_locked(g);
+  }
   delete g;
+  drain_deferred_destroys();
   return 0;
 }
 
@@ -567,6 +577,16 @@ int tnn_graph_info(void* graph, size_t* n_nodes, size_t* n_kernel_nodes, size_t*
   return 0;
 }
 
+static int graph_destroy_now(Graph* g);
+
+// graphs whose owner let go of them in the middle of another capture (Python's garbage collector
+// runs whenever it likes): destroyed once the stream may be synchronised again
+static void drain_deferred_destroys() {
+  std::vector<Graph*> todo;
+  todo.swap(g_deferred_destroy);
+  for (Graph* g : todo) graph_destroy_now(g);
+}
+
 int tnn_graph_destroy(void* graph) {
   Graph* g = (Graph*)graph;
   if (!g) return 0;
@@ -574,6 +594,14 @@ int tnn_graph_destroy(void* graph) {
     delete g;
     return 0;
   }
+  if (g_capture) {      // synchronising the stream now would invalidate the capture in progress
+    g_deferred_destroy.push_back(g);
+    return 0;
+  }
+  return graph_destroy_now(g);
+}
+
+static int graph_destroy_now(Graph* g) {
   cudaStreamSynchronize(ctx().stream);  // a replay may still be running
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
