@@ -15,6 +15,8 @@
 // memory -- one launch, no scratch buffer, no atomics, a fixed summation order.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -245,11 +247,20 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
     const int64_t tiles = (int64_t)grid.x * grid.y;
     // One slab per CTA is one exposed load latency instead of a chain of them, so the slab is as
     // deep as shared memory allows (128 k for float, 64 for double) and, when the tiles leave most
-    // SMs idle, K is cut across a cluster of S CTAs (S <= 8, the portable cluster size) until a
-    // slice fits one slab.
+    // SMs idle, K is cut across a cluster of S CTAs (S <= 4 by default, TNN_SIMT_MAX_SPLIT up to the
+    // portable cluster size of 8) until a slice fits one slab.
     constexpr int SBK = sizeof(T) == 4 ? 128 : 64;
+    static int max_split = -1;
+    if (max_split < 0) {
+      const char* e = getenv("TNN_SIMT_MAX_SPLIT");
+      // measured on the 128x784x200 first MNIST layer (scripts/simt_bench.py): unsplit 26.6 us,
+      // 2-way 18.4, 4-way 12.6, 8-way 16.4 (an 8-CTA cluster is slower to place and to fold)
+      max_split = e ? atoi(e) : 4;
+      if (max_split < 1) max_split = 1;
+      if (max_split > 8) max_split = 8;
+    }
     int64_t S = 1;
-    while (S < 8 && tiles * (S * 2) <= 2 * (int64_t)ctx().sm_count && ceil_div(K, S) > SBK) S *= 2;
+    while (S < max_split && tiles * (S * 2) <= 2 * (int64_t)ctx().sm_count && ceil_div(K, S) > SBK) S *= 2;
     if (S > 1 && grid.y <= 65535) {
       grid.z = (unsigned)S;
       const int64_t kslice = ceil_div(K, S);
