@@ -130,3 +130,24 @@ def test_compute_step_interface():
     for s, g in zip(steps, grads):
         for k in s:
             assert np.allclose(np.asarray(s[k]), -0.5 * g[k])
+
+
+@pytest.mark.parametrize("shape", [(300, 1024), (64, 4096), (257, 516)])
+def test_ce_wide_rows_vectorised_path(shape):
+    """float32 logits and labels with wide rows take the 128-bit row kernel and the unrolled
+    sum-exp pass: loss and gradient against the oracle"""
+    from core.losses import SoftmaxCrossEntropyLoss
+    from core.tensor import Tensor
+    B, C = shape
+    rng = np.random.RandomState(B + C)
+    z = (rng.standard_normal((B, C)) * 2).astype(np.float32)
+    y = np.eye(C, dtype=np.float32)[rng.randint(0, C, B)]
+    y[0] = rng.rand(C).astype(np.float32)            # one soft-label row
+    t = Tensor(z, requires_grad=True)
+    loss = SoftmaxCrossEntropyLoss().loss(t, Tensor(y))
+    loss.backward()
+    rt = R.RefTensor(z.astype(np.float64), requires_grad=True)
+    rl = R.softmax_cross_entropy(rt, y.astype(np.float64))
+    rl.backward()
+    assert op_cases.rel_err(loss.values, rl.values) <= 1e-5
+    assert op_cases.rel_err(t.grad, rt.grad) <= 1e-5

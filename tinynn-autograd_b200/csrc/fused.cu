@@ -170,15 +170,28 @@ ce_partial_sumexp_kernel(const T* z, int64_t n, const T* pmax, int n_pmax, T* ps
   const int64_t nv = n / W;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   T s = T(0);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-    if constexpr (VEC) {
-      typename V4<T>::U a;
-      a.v = reinterpret_cast<const typename V4<T>::type*>(z)[i];
+  if constexpr (VEC) {
+    // four independent 128-bit loads in flight per thread: a one-read stream needs them to reach
+    // HBM bandwidth (measured 3.5 TB/s with one)
+    constexpr int U = 4;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += U * stride) {
+      typename V4<T>::U a[U];
 #pragma unroll
-      for (int k = 0; k < W; ++k) s += m_exp(a.e[k] - mx);
-    } else {
-      s += m_exp(z[i] - mx);
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < nv) a[u].v = reinterpret_cast<const typename V4<T>::type*>(z)[i];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u * stride < nv) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) s += m_exp(a[u].e[k] - mx);
+        }
+      }
     }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride)
+      s += m_exp(z[i] - mx);
   }
   if (VEC && blockIdx.x == 0) {
     int64_t t = nv * W + threadIdx.x;
@@ -228,6 +241,44 @@ ce_rows_kernel(const T* z, const TY* y, int64_t B, int64_t C, const T* stats, T*
     for (int64_t j = lane; j < C; j += 32) {
       TY yy = yr[j];
       if (yy != TY(0)) acc += (m_exp(zr[j] - mx) / S) * (T)yy;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      q[r] = acc;
+      nll[r] = -m_log(acc);
+    }
+  }
+}
+
+// wide float32 rows (C a multiple of 4, 16-byte aligned): a lane takes 4 consecutive columns per
+// 128-bit load, two row chunks (z and y each) in flight; 8 B/element read at HBM speed
+__global__ void __launch_bounds__(256)
+ce_rows_vec_kernel(const float* z, const float* y, int64_t B, int64_t C, const float* stats, float* q,
+                   float* nll) {
+  const float mx = stats[0], S = stats[1];
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  const int64_t nv = C / 4;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < B; r += warps_total) {
+    const float4* zr = reinterpret_cast<const float4*>(z + r * C);
+    const float4* yr = reinterpret_cast<const float4*>(y + r * C);
+    float acc = 0.f;
+    for (int64_t j0 = lane; j0 < nv; j0 += 64) {
+      const int64_t j1 = j0 + 32;
+      const float4 ya = yr[j0], za = zr[j0];
+      float4 yb = make_float4(0.f, 0.f, 0.f, 0.f), zb = yb;
+      if (j1 < nv) {
+        yb = yr[j1];
+        zb = zr[j1];
+      }
+      if (ya.x != 0.f) acc += (m_exp(za.x - mx) / S) * ya.x;
+      if (ya.y != 0.f) acc += (m_exp(za.y - mx) / S) * ya.y;
+      if (ya.z != 0.f) acc += (m_exp(za.z - mx) / S) * ya.z;
+      if (ya.w != 0.f) acc += (m_exp(za.w - mx) / S) * ya.w;
+      if (yb.x != 0.f) acc += (m_exp(zb.x - mx) / S) * yb.x;
+      if (yb.y != 0.f) acc += (m_exp(zb.y - mx) / S) * yb.y;
+      if (yb.z != 0.f) acc += (m_exp(zb.z - mx) / S) * yb.z;
+      if (yb.w != 0.f) acc += (m_exp(zb.w - mx) / S) * yb.w;
     }
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -541,7 +592,16 @@ static int ce_loss_impl(const T* z, const TY* y, int64_t B, int64_t C, const T* 
   if (get_scratch((size_t)B * sizeof(T), &scratch)) return 1;
   T* nll = (T*)scratch;
   int grid = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)ctx().sm_count * 8);
-  ce_rows_kernel<T, TY><<<grid, 256, 0, st>>>(z, y, B, C, stats, q, nll);
+  bool vec = false;
+  if constexpr (sizeof(T) == 4 && sizeof(TY) == 4)
+    vec = C >= 512 && C % 4 == 0 && al16(z) && al16(y);
+  if (vec) {
+    if constexpr (sizeof(T) == 4 && sizeof(TY) == 4)
+      ce_rows_vec_kernel<<<grid, 256, 0, st>>>((const float*)z, (const float*)y, B, C, (const float*)stats,
+                                               (float*)q, nll);
+  } else {
+    ce_rows_kernel<T, TY><<<grid, 256, 0, st>>>(z, y, B, C, stats, q, nll);
+  }
   TNN_POST_LAUNCH();
   ce_fold_loss_kernel<T><<<1, 256, 0, st>>>(nll, B, (T)m, loss);
   TNN_POST_LAUNCH();
