@@ -125,7 +125,10 @@ class Model(object):
                 p._grad, p._grad_zero = gview, not had_grad
             p._grad_host = None
         self._arena = dict(params=list(plist), p=pa, g=ga, slots=slots)
-        self._captured = {}   # recorded steps name the old parameter addresses
+        for st in self._captured.values():   # recorded steps name the old parameter addresses
+            if not isinstance(st, str):
+                st.destroy()
+        self._captured = {}
         return True
 
     # ------------------------------------------------------------------ training step
@@ -186,8 +189,18 @@ class Model(object):
         from core.tensor import Tensor
         x = inputs if isinstance(inputs, Tensor) else Tensor(inputs)
         y = targets if isinstance(targets, Tensor) else Tensor(targets)
-        key = (x.shape, x.dtype.str, y.shape, y.dtype.str, dist.world_size())
+        key = (x.shape, x.dtype.str, y.shape, y.dtype.str, dist.world_size(), id(self.optimizer),
+               id(self.loss), self._phase)
         state = self._captured.get(key)
+        if state is not None and not isinstance(state, str):
+            # a recorded step names the parameter arenas: if a parameter was rebound since
+            # (p.values = ..., load(), set_parameters) every recording is stale
+            if not self._arena_valid(self._param_list()):
+                for st in self._captured.values():
+                    if not isinstance(st, str):
+                        st.destroy()
+                self._captured = {}
+                state = None
         if state is None or state == "eager":
             loss = self._eager_step(x, y)
             if state is None:

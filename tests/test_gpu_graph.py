@@ -169,3 +169,24 @@ def test_graph_destroyed_during_another_capture_is_deferred():
     x = np.arange(8, dtype=np.float32)
     assert np.array_equal(be.to_numpy(d), x * x + x)
     g2.destroy()
+
+
+def test_recorded_step_is_dropped_when_a_parameter_is_rebound():
+    """p.values = ... moves a parameter out of the arena a recorded step names: the next
+    train_step must notice, fall back to the eager lines and record again -- same numbers as a
+    model that never used a graph"""
+    batches = _batches(0, 32, 10, [16] * 10)
+    net_a, model_a = _model([64, 10], 7, d_in=32)
+    net_b, model_b = _model([64, 10], 7, d_in=32)
+    for i, (x, y) in enumerate(batches):
+        if i == 5:
+            for net in (net_a, net_b):
+                w = net.layers[0].params["w"]
+                w.values = w.values * 0.5
+                w.zero_grad()
+        la = float(_eager(model_a, x, y).values)
+        lb = float(model_b.train_step(x, y).values)
+        assert la == lb, i
+    for pa, pb in zip(_params(net_a), _params(net_b)):
+        assert np.array_equal(pa, pb)
+    assert any(hasattr(s, "graph") for s in model_b._captured.values())
