@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 namespace tnn {
 
 // One output tile.  SPLITK: gridDim.z CTAs (one cluster) share the tile, CTA z covers k in
-// [z*kslice, ...).  A == nullptr stands for a matrix of ones (the bias gradient 1^T g as a product).
+// [z*kslice, ...).
 template <typename T, int BM, int BN, int BK, int TM, int TN, bool SPLITK>
 __device__ __forceinline__ void
 gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restrict__ C, int64_t ldc,
@@ -50,39 +50,48 @@ gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restric
 
   T ra[A_PER], rb[B_PER];
 
+  // Element e of this thread's share of a slab is element `tid + e*NT` of the tile.  With NT a
+  // multiple of BK, BM and BN the (row, k) of element e is (row0 + e*drow, k0 + e*dk): one of the
+  // two advances is zero, so every load is `base + e*step` behind two compares.  (Written out by
+  // hand: left to the compiler, the div/mod per element and the runtime layout select were 2,000
+  // integer instructions around 44 loads, and the MNIST-sized products are issue-bound.)
+  static_assert(NT % BK == 0 && NT % BM == 0 && NT % BN == 0, "strength-reduced tile loads");
+  const int a_m = a_kfast ? tid / BK : tid % BM, a_k = a_kfast ? tid % BK : tid / BM;
+  const int a_dm = a_kfast ? NT / BK : 0, a_dk = a_kfast ? 0 : NT / BM;
+  const int b_k = b_nfast ? tid / BN : tid % BK, b_n = b_nfast ? tid % BN : tid / BK;
+  const int b_dk = b_nfast ? NT / BN : 0, b_dn = b_nfast ? 0 : NT / BK;
+  const T* a_base = A + (m0 + a_m) * a_rs + (int64_t)a_k * a_cs;
+  const T* b_base = B + (int64_t)b_k * b_rs + (n0 + b_n) * b_cs;
+  const int64_t a_step = (int64_t)a_dm * a_rs + (int64_t)a_dk * a_cs;
+  const int64_t b_step = (int64_t)b_dk * b_rs + (int64_t)b_dn * b_cs;
+  // bounds as 32-bit counts (clamped): one integer compare per load instead of a 64-bit pair
+  auto clamp32 = [](int64_t v) { return (int)(v > (1 << 30) ? (1 << 30) : (v < -1 ? -1 : v)); };
+  const int a_rows_left = clamp32(M - m0 - a_m);   // row e*a_dm is valid while e*a_dm < a_rows_left
+  const int b_cols_left = clamp32(N - n0 - b_n);
+
   auto load_tiles = [&](int64_t k0) {
+    const T* ap = a_base + k0 * a_cs;
+    const T* bp = b_base + k0 * b_rs;
+    const int a_k_left = clamp32(K - k0 - a_k), b_k_left = clamp32(K - k0 - b_k);
 #pragma unroll
     for (int e = 0; e < A_PER; ++e) {
-      int idx = tid + e * NT;
-      int m = a_kfast ? idx / BK : idx % BM;
-      int k = a_kfast ? idx % BK : idx / BM;
-      int64_t gm = m0 + m, gk = k0 + k;
-      ra[e] = (gm < M && gk < K) ? (A ? A[gm * a_rs + gk * a_cs] : T(1)) : T(0);
+      const bool ok = e * a_dm < a_rows_left && e * a_dk < a_k_left;
+      ra[e] = ok ? ap[e * a_step] : T(0);
     }
 #pragma unroll
     for (int e = 0; e < B_PER; ++e) {
-      int idx = tid + e * NT;
-      int k = b_nfast ? idx / BN : idx % BK;
-      int n = b_nfast ? idx % BN : idx / BK;
-      int64_t gk = k0 + k, gn = n0 + n;
-      rb[e] = (gk < K && gn < N) ? B[gk * b_rs + gn * b_cs] : T(0);
+      const bool ok = e * b_dk < b_k_left && e * b_dn < b_cols_left;
+      rb[e] = ok ? bp[e * b_step] : T(0);
     }
   };
+  T* const as_base = &As[a_k][a_m];
+  T* const bs_base = &Bs[b_k][b_n];
+  const int as_step = a_dk * (BM + 1) + a_dm, bs_step = b_dk * (BN + 1) + b_dn;
   auto store_tiles = [&]() {
 #pragma unroll
-    for (int e = 0; e < A_PER; ++e) {
-      int idx = tid + e * NT;
-      int m = a_kfast ? idx / BK : idx % BM;
-      int k = a_kfast ? idx % BK : idx / BM;
-      As[k][m] = ra[e];
-    }
+    for (int e = 0; e < A_PER; ++e) as_base[e * as_step] = ra[e];
 #pragma unroll
-    for (int e = 0; e < B_PER; ++e) {
-      int idx = tid + e * NT;
-      int k = b_nfast ? idx / BN : idx % BK;
-      int n = b_nfast ? idx % BN : idx / BK;
-      Bs[k][n] = rb[e];
-    }
+    for (int e = 0; e < B_PER; ++e) bs_base[e * bs_step] = rb[e];
   };
 
   int64_t k_begin = 0;
@@ -222,6 +231,24 @@ gemm_simt_group_kernel(const SimtGroup<T> grp) {
     if (i < grp.count && (int)blockIdx.x >= grp.p[i].first) pi = i;
   const SimtProblem<T>& q = grp.p[pi];
   const int local = (int)blockIdx.x - q.first;
+  if (q.A == nullptr) {
+    // bias gradient: column sums of B[K, N] for 32 columns.  8 row lanes per column, folded in a
+    // fixed order through shared memory (deterministic)
+    const int col = local * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+    T acc = T(0);
+    if (col < q.N)
+      for (int64_t r = lane; r < q.K; r += 8) acc += q.B[r * q.b_rs + col * q.b_cs];
+    As[lane][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (lane == 0 && col < q.N) {
+      T v = As[0][col & 31];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) v += As[i][col & 31];
+      if (q.flags & 1) v += q.C[col];
+      q.C[col] = v;
+    }
+    return;
+  }
   gemm_tile<T, 32, 32, BK, 2, 2, false>(As, Bs, local % q.tiles_x, local / q.tiles_x, q.C, q.ldc, q.A, q.a_rs,
                                         q.a_cs, q.B, q.b_rs, q.b_cs, q.M, q.N, q.K, nullptr, q.flags,
                                         q.act_out, q.mask_src, 0);
