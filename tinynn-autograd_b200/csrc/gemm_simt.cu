@@ -23,11 +23,19 @@ namespace cg = cooperative_groups;
 
 namespace tnn {
 
+// shared-memory row pitch: even for the 2x2 micro-tile so a thread's two A (or B) values of one k are
+// ONE 64/128-bit load (2-way store conflict in the k-fast layout, 16 stores per slab: cheap), odd
+// (conflict-free) otherwise
+template <int B, int TT>
+struct Pitch {
+  static constexpr int value = B + (TT == 2 ? 2 : 1);
+};
+
 // One output tile.  SPLITK: gridDim.z CTAs (one cluster) share the tile, CTA z covers k in
 // [z*kslice, ...).
 template <typename T, int BM, int BN, int BK, int TM, int TN, bool SPLITK>
 __device__ __forceinline__ void
-gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restrict__ C, int64_t ldc,
+gemm_tile(T (*As)[Pitch<BM, TM>::value], T (*Bs)[Pitch<BN, TN>::value], int tile_x, int tile_y, T* __restrict__ C, int64_t ldc,
           const T* __restrict__ A, int64_t a_rs, int64_t a_cs, const T* __restrict__ B, int64_t b_rs,
           int64_t b_cs, int64_t M, int64_t N, int64_t K, const T* __restrict__ bias, int flags,
           T* __restrict__ act_out, const T* __restrict__ mask_src, int64_t kslice) {
@@ -73,20 +81,27 @@ gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restric
     const T* ap = a_base + k0 * a_cs;
     const T* bp = b_base + k0 * b_rs;
     const int a_k_left = clamp32(K - k0 - a_k), b_k_left = clamp32(K - k0 - b_k);
+    int rl = a_rows_left, kl = a_k_left;       // running bounds and pointers: adds, no multiplies
 #pragma unroll
     for (int e = 0; e < A_PER; ++e) {
-      const bool ok = e * a_dm < a_rows_left && e * a_dk < a_k_left;
-      ra[e] = ok ? ap[e * a_step] : T(0);
+      ra[e] = (rl > 0 && kl > 0) ? *ap : T(0);
+      rl -= a_dm;
+      kl -= a_dk;
+      ap += a_step;
     }
+    int cl = b_cols_left;
+    kl = b_k_left;
 #pragma unroll
     for (int e = 0; e < B_PER; ++e) {
-      const bool ok = e * b_dk < b_k_left && e * b_dn < b_cols_left;
-      rb[e] = ok ? bp[e * b_step] : T(0);
+      rb[e] = (cl > 0 && kl > 0) ? *bp : T(0);
+      cl -= b_dn;
+      kl -= b_dk;
+      bp += b_step;
     }
   };
   T* const as_base = &As[a_k][a_m];
   T* const bs_base = &Bs[b_k][b_n];
-  const int as_step = a_dk * (BM + 1) + a_dm, bs_step = b_dk * (BN + 1) + b_dn;
+  const int as_step = a_dk * Pitch<BM, TM>::value + a_dm, bs_step = b_dk * Pitch<BN, TN>::value + b_dn;
   auto store_tiles = [&]() {
 #pragma unroll
     for (int e = 0; e < A_PER; ++e) as_base[e * as_step] = ra[e];
@@ -111,10 +126,17 @@ gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restric
 #pragma unroll 8
     for (int kk = 0; kk < depth; ++kk) {
       T a[TM], b[TN];
+      if constexpr (TM == 2 && TN == 2) {
+        struct alignas(2 * sizeof(T)) Pair { T v[2]; };
+        const Pair pa = *reinterpret_cast<const Pair*>(&As[kk][ty * 2]);
+        const Pair pb = *reinterpret_cast<const Pair*>(&Bs[kk][tx * 2]);
+        a[0] = pa.v[0]; a[1] = pa.v[1]; b[0] = pb.v[0]; b[1] = pb.v[1];
+      } else {
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+        for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+      }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -127,7 +149,7 @@ gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restric
     // partial tile -> own shared memory; CTA 0 folds the cluster's partials in rank order
     static_assert(BK >= BN, "the partial tile reuses the As slab");
     cg::cluster_group cluster = cg::this_cluster();
-    T (*part)[BM + 1] = As;    // As is [BK][BM+1]: rows 0..BN-1 hold the BN x BM partial (BK >= BN)
+    auto part = As;            // rows 0..BN-1 of the A slab hold the BN x BM partial (BK >= BN)
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -141,7 +163,7 @@ gemm_tile(T (*As)[BM + 1], T (*Bs)[BN + 1], int tile_x, int tile_y, T* __restric
 #pragma unroll
       for (unsigned r = 1; r < 8; ++r) {
         if (r < S) {
-          T (*peer)[BM + 1] = reinterpret_cast<T (*)[BM + 1]>(cluster.map_shared_rank(&As[0][0], r));
+          auto peer = reinterpret_cast<T (*)[Pitch<BM, TM>::value]>(cluster.map_shared_rank(&As[0][0], r));
 #pragma unroll
           for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -190,8 +212,8 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
                  const T* __restrict__ B, int64_t b_rs, int64_t b_cs, int64_t M, int64_t N, int64_t K,
                  const T* __restrict__ bias, int flags, T* __restrict__ act_out,
                  const T* __restrict__ mask_src, int64_t kslice) {
-  __shared__ T As[BK][BM + 1];
-  __shared__ T Bs[BK][BN + 1];
+  __shared__ __align__(16) T As[BK][Pitch<BM, TM>::value];
+  __shared__ __align__(16) T Bs[BK][Pitch<BN, TN>::value];
   gemm_tile<T, BM, BN, BK, TM, TN, SPLITK>(As, Bs, (int)blockIdx.x, (int)blockIdx.y, C, ldc, A, a_rs, a_cs,
                                            B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, kslice);
 }
@@ -223,8 +245,8 @@ struct SimtGroup {
 template <typename T, int BK>
 __global__ void __launch_bounds__(256, 2)
 gemm_simt_group_kernel(const SimtGroup<T> grp) {
-  __shared__ T As[BK][33];
-  __shared__ T Bs[BK][33];
+  __shared__ __align__(16) T As[BK][Pitch<32, 2>::value];
+  __shared__ __align__(16) T Bs[BK][Pitch<32, 2>::value];
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < 3; ++i)
