@@ -319,20 +319,32 @@ __device__ __forceinline__ T block1024_reduce_first8(T v, T* sm /* >= 32 */) {
   return r;
 }
 
+constexpr int CE_SMALL_STAGE_BYTES = 16384;   // logits staged in shared memory when they fit (MNIST: 1280 values)
 template <typename T, typename TY>
 __global__ void __launch_bounds__(1024)
 ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats, T* q, T* loss) {
   __shared__ T sm[32];
   __shared__ T nll[CE_SMALL_MAX_ROWS];
+  constexpr int CE_SMALL_STAGE = CE_SMALL_STAGE_BYTES / (int)sizeof(T);
+  __shared__ T zs[CE_SMALL_STAGE];
   const int64_t n = B * C;
   const bool first = threadIdx.x < 256;
+  // one trip to global memory for the logits when they fit in shared memory: the max pass, the
+  // sum-exp pass and the per-row pass then read the staged copy (three dependent round trips
+  // were most of this kernel's 9 us)
+  const bool staged = n <= CE_SMALL_STAGE;
+  if (staged) {
+    for (int64_t i = threadIdx.x; i < n; i += 1024) zs[i] = z[i];
+    __syncthreads();
+  }
+  const T* zz = staged ? zs : z;
   T mx = -INFINITY;
   if (first)
-    for (int64_t i = threadIdx.x; i < n; i += 256) mx = m_max(mx, z[i]);
+    for (int64_t i = threadIdx.x; i < n; i += 256) mx = m_max(mx, zz[i]);
   mx = block1024_reduce_first8<T, true>(mx, sm);
   T S = T(0);
   if (first)
-    for (int64_t i = threadIdx.x; i < n; i += 256) S += m_exp(z[i] - mx);
+    for (int64_t i = threadIdx.x; i < n; i += 256) S += m_exp(zz[i] - mx);
   S = block1024_reduce_first8<T, false>(S, sm);
   if (threadIdx.x == 0) {
     stats[0] = mx;
@@ -347,7 +359,7 @@ ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats
       const int64_t r = r0 + 32 * u;
       acc[u] = T(0);
       if (r < B) {
-        const T* zr = z + r * C;
+        const T* zr = zz + r * C;
         const TY* yr = y + r * C;
         for (int64_t j = lane; j < C; j += 32) {
           TY yy = yr[j];
