@@ -208,21 +208,51 @@ def pool_stats():
 # --------------------------------------------------------------------------------------------
 # device memory
 # --------------------------------------------------------------------------------------------
+# Small blocks are recycled on the Python side: a freed block of a 512-byte size class is kept in a
+# list and handed to the next request of that class without crossing into the library (two ctypes
+# calls saved per op result; the MNIST-sized step makes ~20 such allocations and is host-bound).
+# Same single-stream ordering argument as the C pool.  Blocks born inside a graph capture belong
+# to that graph and never enter this cache; during a capture the cache is bypassed entirely.
+_SMALL_MAX = 1 << 20          # the range the C pool rounds to 512-byte classes
+_SMALL_KEEP = 64              # blocks kept per class up to 64 KiB; 8 per class above that
+_small_free = {}
+_capturing = False
+
+
 class _Buf(object):
     """Owner of one pool block; freed back to the pool when the last view dies."""
-    __slots__ = ("ptr", "nbytes", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "klass", "__weakref__")
 
     def __init__(self, nbytes):
+        self.nbytes = nbytes
+        if nbytes <= _SMALL_MAX and not _capturing:
+            klass = (nbytes + 511) & ~511
+            lst = _small_free.get(klass)
+            if lst:
+                self.ptr = lst.pop()
+                self.klass = klass
+                return
+            nbytes = klass
+            self.klass = klass
+        else:
+            self.klass = 0
         ptr = _lib.tnn_alloc_ptr(nbytes)
         if not ptr:
+            self.ptr = None
             _raise("tnn_alloc")
         self.ptr = ptr
-        self.nbytes = nbytes
 
     def __del__(self):
         try:
-            if self.ptr and _lib is not None:
-                _lib.tnn_free(self.ptr)
+            ptr = self.ptr
+            if not ptr or _lib is None:
+                return
+            if self.klass and not _capturing:
+                lst = _small_free.setdefault(self.klass, [])
+                if len(lst) < (_SMALL_KEEP if self.klass <= 65536 else 8):
+                    lst.append(ptr)
+                    return
+            _lib.tnn_free(ptr)
         except Exception:
             pass
 
@@ -1075,6 +1105,7 @@ class _Capture(object):
             raise BackendError("StepGraph already holds a captured step")
         # the cyclic garbage collector must not run finalisers (which may synchronise the stream or
         # free pinned memory) in the middle of a capture: collect now, pause it until the end
+        global _capturing
         gc.collect()
         self._gc_was_enabled = gc.isenabled()
         gc.disable()
@@ -1082,9 +1113,12 @@ class _Capture(object):
             if self._gc_was_enabled:
                 gc.enable()
             _raise("tnn_graph_begin")
+        _capturing = True
         return self.graph
 
     def __exit__(self, exc_type, exc, tb):
+        global _capturing
+        _capturing = False
         try:
             if exc_type is not None:
                 _lib.tnn_graph_abort()
