@@ -418,3 +418,63 @@ def test_grouped_dense_backward_matches_separate_launches(dtype):
     assert op_cases.rel_err(out[True][3], out[False][3]) <= tol      # non-leaf .grad of a pre-activation
     for a, b in zip(out[True][0], out[True][1]):
         assert op_cases.rel_err(b, 2 * a) <= 10 * tol                # second backward doubled it
+
+
+@pytest.mark.parametrize("split", ["mix", "tf32x3"])
+def test_tensor_core_mlp_teacher_forced_over_steps(split):
+    """the tcgen05 path along a training run: 12 steps of a 3-layer 256-wide MLP at batch 512, the
+    oracle's (Adam-updated, float32-rounded) parameters loaded into the engine before every step,
+    loss within 1e-5 and every gradient within rel 1e-5 of the oracle's at each step -- for both
+    operand splits.  A step on which a pre-activation sits so close to zero that float32 and
+    float64 arithmetic put it on different sides of the ReLU kink (one unit in ~10^6, seen about
+    once per run) compares the loss only: there the gradients differ by the discontinuity, not by
+    the arithmetic."""
+    import core._backend as be
+    from core.tensor import Tensor
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 1 << 20, split
+    try:
+        rng = np.random.RandomState(8)
+        B, D = 512, 256
+        np.random.seed(8)
+        mlp = R.RefMLP([D, D, D], R.RefAdam(lr=1e-3))
+        net, model, loss_layer = _build([D, D, D])
+        compared = 0
+        for it in range(12):
+            x = rng.rand(B, D).astype(np.float32)
+            labels = np.eye(D, dtype=np.float32)[rng.randint(0, D, B)]
+            mlp.zero_grad()
+            h, ref_pre = R.lift(x), []
+            for layer in mlp.layers:
+                h = layer.forward(h)
+                if isinstance(layer, R.RefDense):
+                    ref_pre.append(h.values)
+            rloss = R.softmax_cross_entropy(h, labels)
+            rloss.backward()
+            if it == 0:
+                model.forward(Tensor(x))          # lazy initialisation of the engine's layers
+            params = [p for layer in net.get_parameters() for p in layer.values()]
+            for p, rp in zip(params, mlp.params()):
+                p.values = rp.values.astype(np.float32)
+                p.requires_grad = True
+            model.zero_grad()
+            assert be.use_tensor_cores(B, D, D, be.F32)
+            loss = loss_layer.loss(model.forward(Tensor(x)), Tensor(labels))
+            loss.backward()
+            assert abs(float(loss.values) - float(rloss.values)) <= 1e-5, it
+            pre = [layer.inputs.values for layer in net.layers if layer.name == "ReLU"]
+            same_side = all(np.array_equal(z >= 0, zr >= 0) for z, zr in zip(pre, ref_pre))
+            for z, zr in zip(pre, ref_pre):
+                assert op_cases.rel_err(z, zr) <= 1e-5, it
+            if same_side:
+                compared += 1
+                for p, rp in zip(params, mlp.params()):
+                    assert op_cases.rel_err(p.grad, rp.grad) <= 1e-5, it
+            mlp.step()
+            # both sides start the next step from bit-identical parameters: the oracle keeps the
+            # float32 rounding of its update
+            for rp in mlp.params():
+                rp.assign(rp.values.astype(np.float32).astype(np.float64))
+        assert compared >= 9
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
