@@ -3,7 +3,7 @@
 step()/zero_grad() keep the reference semantics (model.py:45-68) on top of two flat device
 arenas -- one for every parameter, one for every gradient, laid out in the reference's flatten
 order (layers in order, `w` then `b`, optimizer.py:14-15):
-  * zero_grad()  = one memset of the gradient arena
+  * zero_grad()  = flags only (a slot is overwritten by the first gradient of the step)
   * backward     = GEMM / column-sum kernels write parameter gradients straight into their slots
   * step()       = (data parallel: one NCCL all-reduce of the gradient arena) + one fused
                    optimiser kernel over the arenas
@@ -137,6 +137,9 @@ class Model(object):
         fused = self._arena_valid(plist) or self._build_arena(plist)
         if fused and all(p._grad is p._gslot for p in plist):
             a = self._arena
+            for p in plist:
+                if p._grad_zero:             # no gradient reached this parameter in this step
+                    be.memset_zero(p._gslot)
             if dist.world_size() > 1:
                 # SUM (1/m_global is already inside dL/dz), in chunks pipelined with the optimiser
                 dist.reduce_and_apply(self.optimizer, a["p"], a["g"], _ALIGN)
@@ -156,8 +159,8 @@ class Model(object):
             grad = dict()
             for k in param:
                 p = param[k]
-                if p._grad is None:
-                    grad[k] = be.zeros(p.shape, p.dtype) if p._grad_zero else None
+                if p._grad_zero:
+                    grad[k] = be.zeros(p.shape, p.dtype)
                 else:
                     grad[k] = p._grad
                 if grad[k] is None:
@@ -237,7 +240,8 @@ class Model(object):
         be.new_split_epoch()
         plist = self._param_list()
         if plist and self._arena_valid(plist):
-            be.memset_zero(self._arena["g"])
+            # no memset of the arena: the backward pass overwrites every slot it reaches (the first
+            # write of a step does not accumulate) and step() clears the ones it did not reach
             for p in plist:
                 p._grad, p._grad_zero, p._grad_host = p._gslot, True, None
             return

@@ -87,12 +87,12 @@ class Tensor(object):
     @property
     def grad(self):
         """host copy of the accumulated gradient, or None (tensor.py:22)"""
-        if self._grad is None:
-            if not self._grad_zero:
-                return None
-            if self._grad_host is None:
+        if self._grad_zero:      # zeroed and nothing accumulated since (an arena slot is not
+            if self._grad_host is None:   # cleared until something is written or the step needs it)
                 self._grad_host = np.zeros(self.shape, dtype=self._data.dtype)
             return self._grad_host
+        if self._grad is None:
+            return None
         if self._grad_host is None:
             self._grad_host = be.to_numpy(self._grad)
         return self._grad_host
@@ -253,7 +253,8 @@ class Tensor(object):
         """tensor.py:170-171.  Lazy: nothing is allocated until a gradient arrives."""
         self._grad_host = None
         if self._gslot is not None:
-            be.memset_zero(self._gslot)
+            # the slot is not cleared here: the first gradient overwrites it, and Model.step clears
+            # the slots that received none (while _grad_zero is set the slot's content is undefined)
             self._grad = self._gslot
             self._grad_zero = True
         else:
