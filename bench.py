@@ -299,9 +299,12 @@ def run_b200_arm(args, cfg):
     t0 = time.perf_counter()
     e0, e1 = be.Event(), be.Event()
     e0.record()
+    batch = next(feed)
     for _ in range(e2e_steps):
-        batch = next(feed)                               # H2D of the NEXT batch is queued in here
-        float(train_step(batch.inputs, batch.targets).values)   # D2H read of the loss
+        loss = train_step(batch.inputs, batch.targets)   # queued; the GPU starts on it
+        batch = next(feed)                               # H2D of a following batch is queued in here,
+                                                         # while the GPU runs the step just queued
+        float(loss.values)                               # D2H read of this step's loss
     e1.record()
     dist.barrier()
     e2e_ms = e1.elapsed_ms_since(e0)
