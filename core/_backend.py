@@ -215,7 +215,9 @@ def pool_stats():
 # to that graph and never enter this cache; during a capture the cache is bypassed entirely.
 _SMALL_MAX = 1 << 20          # the range the C pool rounds to 512-byte classes
 _SMALL_KEEP = 64              # blocks kept per class up to 64 KiB; 8 per class above that
+_SMALL_CAP_BYTES = 256 << 20  # total bytes this cache may hold back from the library's pool
 _small_free = {}
+_small_bytes = 0
 _capturing = False
 
 
@@ -229,6 +231,8 @@ class _Buf(object):
             klass = (nbytes + 511) & ~511
             lst = _small_free.get(klass)
             if lst:
+                global _small_bytes
+                _small_bytes -= klass
                 self.ptr = lst.pop()
                 self.klass = klass
                 return
@@ -248,9 +252,12 @@ class _Buf(object):
             if not ptr or _lib is None:
                 return
             if self.klass and not _capturing:
+                global _small_bytes
                 lst = _small_free.setdefault(self.klass, [])
-                if len(lst) < (_SMALL_KEEP if self.klass <= 65536 else 8):
+                if (len(lst) < (_SMALL_KEEP if self.klass <= 65536 else 8)
+                        and _small_bytes + self.klass <= _SMALL_CAP_BYTES):
                     lst.append(ptr)
+                    _small_bytes += self.klass
                     return
             _lib.tnn_free(ptr)
         except Exception:
