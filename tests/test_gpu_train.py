@@ -478,3 +478,27 @@ def test_tensor_core_mlp_teacher_forced_over_steps(split):
         assert compared >= 9
     finally:
         be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-6), (np.float64, 1e-12)])
+def test_tanh_and_sigmoid_layers(dtype, tol):
+    """layers.py:74-89: Tanh is (1 - e^-x) / (1 + e^-x) = tanh(x / 2) (the reference's formula, kept),
+    Sigmoid is 1 / (1 + e^-x) (raises upstream; works here): values and gradients in closed form"""
+    from core.layers import Sigmoid, Tanh
+    from core.tensor import Tensor
+    rng = np.random.RandomState(6)
+    x = (rng.standard_normal((37, 21)) * 2).astype(dtype)
+    g = rng.standard_normal((37, 21)).astype(dtype)
+    x64, g64 = x.astype(np.float64), g.astype(np.float64)
+    t = Tensor(x, requires_grad=True)
+    out = Tanh().forward(t)
+    out.backward(g)
+    ref = np.tanh(x64 / 2)
+    assert op_cases.rel_err(out.values, ref) <= tol
+    assert op_cases.rel_err(t.grad, g64 * 0.5 * (1 - ref ** 2)) <= 10 * tol
+    s = Tensor(x, requires_grad=True)
+    out = Sigmoid().forward(s)
+    out.backward(g)
+    ref = 1 / (1 + np.exp(-x64))
+    assert op_cases.rel_err(out.values, ref) <= tol
+    assert op_cases.rel_err(s.grad, g64 * ref * (1 - ref)) <= 10 * tol
