@@ -310,6 +310,37 @@ class DArray(object):
         return "DArray(shape=%s, dtype=%s)" % (self.shape, self.dtype.name)
 
 
+class LazyReLU(DArray):
+    """max(src, 0) that is only computed if somebody asks for its address.  The fused Dense+ReLU
+    launch of the tensor-core path hands the activation on as operand planes (attached as `.split`);
+    in a training step nothing reads the fp32 activation itself -- the next products use the planes,
+    the backward mask uses the pre-activation -- so its 4 B/element are not written unless needed
+    (`.values`, a product outside the cached step, a SIMT consumer)."""
+    __slots__ = ("_src", "_real")
+
+    def __init__(self, src):
+        self._src = src
+        self._real = None
+        self.shape = src.shape
+        self.dtype = src.dtype
+        self.size = src.size
+        self.split = None
+        self.aux = None
+
+    def _materialise(self):
+        if self._real is None:
+            self._real = relu_fwd(self._src)
+        return self._real
+
+    @property
+    def ptr(self):
+        return self._materialise().ptr
+
+    @property
+    def buf(self):
+        return self._materialise().buf
+
+
 def device_dtype(np_dtype):
     """dtype policy: float32 stays float32; everything else (ints, bools, float64, Python
     numbers) is computed in float64 so the reference's exact-equality tests hold."""
@@ -656,6 +687,8 @@ TC_MN_MAJOR = os.environ.get("TNN_TC_MN_MAJOR", "1") != "0"   # 0: transposed tf
 # operand split of the tensor-core product: "mix" = tf32 main term + bf16 cross terms (default),
 # "tf32x3" = three tf32 MMAs per K step (the textbook 3xTF32, kept as cross-check)
 TC_SPLIT = os.environ.get("TNN_GEMM_SPLIT", "mix")
+# fused Dense+ReLU launch on the tensor-core path: do not write the fp32 activation (see LazyReLU)
+LAZY_RELU_OUT = os.environ.get("TNN_LAZY_RELU", "1") != "0"
 BF16_BYTES = 2
 _split_epoch = 0
 
@@ -788,10 +821,13 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         if act:
             act_hi = empty((M, ld_act), F32)
             act_h16, act_l16 = _empty_bf16(M, ld_act), _empty_bf16(M, ld_act)
+            if LAZY_RELU_OUT and mask_src is None:
+                act_out = LazyReLU(out)      # planes only: the fp32 activation is not written
         if _lib.tnn_gemm_tf32_bf16x2(out.ptr, N, a_hi.ptr, a_h16.ptr, a_l16.ptr, lda, b_hi.ptr,
                                      b_h16.ptr, b_l16.ptr, ldb, M, N, K,
                                      bias.ptr if bias is not None else None, flags, layout,
-                                     act_out.ptr if act else None, act_hi.ptr if act else None,
+                                     act_out.ptr if (act and type(act_out) is not LazyReLU) else None,
+                                     act_hi.ptr if act else None,
                                      act_h16.ptr if act else None, act_l16.ptr if act else None,
                                      ld_act, mask_src.ptr if (act and mask_src is not None) else None):
             _raise("tnn_gemm_tf32_bf16x2")

@@ -200,7 +200,8 @@ int tnn_split_tf32(const float* x, int64_t R, int64_t C,
  * Fused activation outputs (Dense -> ReLU -> next Dense without extra passes, layers.py:49,97-98):
  * act_out (may be NULL, pitch ldd) receives ReLU(D) while D keeps the pre-activation the ReLU
  * backward mask needs; act_hi/act_lo (may be NULL, pitch ld_act) receive the tf32 planes of
- * ReLU(D), i.e. the A operand of the next layer's product.
+ * ReLU(D), i.e. the A operand of the next layer's product.  act_out may be NULL while the planes
+ * are given: the fp32 ReLU output is then not written at all (nothing in a training step reads it).
  * Backward form: with mask_src (pitch ldd) set, act_out = D * (mask_src >= 0) instead -- the dX
  * product of a layer whose input came out of a ReLU hands back both dL/da (D) and dL/dz (act_out,
  * with tf32 planes for the dW / dX products it feeds), ops.py:342-343 fused into ops.py:156-157. */

@@ -574,7 +574,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       decode(u, t, sp, kb_begin, kb_end);
       const bool accumulate = (flags & 1) || sp > 0;
       // the unit that holds the complete sum also emits the fused activation outputs
-      const bool emit_act = act_out != nullptr && (u < t_full || sp + 1 == tail_split);
+      // act_out may be NULL with the planes present: the fp32 ReLU output is then never written
+      // (the next products read its planes, the backward mask reads the pre-activation)
+      const bool emit_act = (act_out != nullptr || act_hi != nullptr) && (u < t_full || sp + 1 == tail_split);
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
       tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
@@ -710,7 +712,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     a = make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y,
                                     v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
                   }
-                  *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = a;
+                  if (act_out) *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = a;
                   if (act_hi) {
                     const float4 h = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
                     *reinterpret_cast<float4*>(act_hi + (int64_t)grow * ld_act + gcol) = h;
@@ -743,7 +745,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                       float a;
                       if (mask_src) a = mask_src[(int64_t)grow * ldd + gcol + k] >= 0.f ? x : x * 0.f;
                       else a = x < 0.f ? 0.f : x;
-                      act_out[(int64_t)grow * ldd + gcol + k] = a;
+                      if (act_out) act_out[(int64_t)grow * ldd + gcol + k] = a;
                       if (act_hi) {
                         const float h = to_tf32(a);
                         act_hi[(int64_t)grow * ld_act + gcol + k] = h;
@@ -1078,7 +1080,8 @@ static int gemm_common(const char* who, bool mix, float* D, int64_t ldd, const t
     env_read = true;
   }
   tc::ActOut act = act_in;
-  if (act.out) {
+  if (!act.out && act.hi && act.mask_src) TNN_FAIL(std::string(who) + ": the mask_src form needs act_out");
+  if (act.out || act.hi) {
     const int64_t need = mix ? 8 : 4;
     if ((act.hi == nullptr) != (act.lo == nullptr)) TNN_FAIL(std::string(who) + ": activation planes come together");
     if (mix && (act.hi == nullptr) != (act.l16 == nullptr)) TNN_FAIL(std::string(who) + ": activation planes come together");
