@@ -1,39 +1,62 @@
 """Benchmark of the hot path: MLP train samples/sec (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload wide|mnist] [--batch-per-gpu B]
+                    [--workload wide|mnist] [--batch-per-gpu B] [--global-batch G]
 
 Workload at N=1 (default): BASELINE.json configs[3] -- 4 x Dense(4096) with 3 ReLU, D_in = C =
-4096, batch 8192, fp32 storage, 3xTF32 tensor-core GEMMs, fused global-softmax CE, fused Adam;
-synthetic data and reference-style Xavier-uniform weights (np.random.seed(0)).
+4096, batch 8192, fp32 storage, fp32-accurate split tensor-core GEMMs, fused global-softmax CE,
+fused Adam; synthetic data and reference-style Xavier-uniform weights (np.random.seed(0)).
 At N>1 (launched with torchrun, one rank per GPU): the same model, batch 8192 PER GPU (weak
 scaling; N=8 is configs[4]'s global batch 65536), rows sharded by rank, one NCCL SUM all-reduce
 of the flat gradient arena per step plus the 2-float CE-normaliser all-gather.
 
 A "step" = zero_grad + forward + loss + backward + (all-reduce) + optimizer step.
   value : steps timed with CUDA events on the compute stream, inputs resident in HBM
-  e2e   : the same step driven from HOST buffers: per step the batch (inputs + one-hot labels)
-          is copied from pinned host memory, and the loss is read back to the host
+  e2e   : the same step driven from HOST buffers through utils.data_iterator.PrefetchIterator:
+          per step the batch (float32 inputs + int32 class labels, one-hot rows built on the
+          device) is copied from pinned host memory, and the loss is read back to the host
   roofline     : the tcgen05 GEMM kernel, per-launch time from CUDA events inside the timed steps
-  cpu_baseline : oracle/ref_numpy.py (numpy restatement of the reference) on the host cores, on a
-                 bounded sample (rank 0, N=1 only)
---impl reference times that CPU implementation alone, on the same config/metric/unit.
-"""
-import argparse
-import json
-import os
-import subprocess
-import sys
-import threading
-import time
+  cpu_baseline : oracle/ref_numpy.py (numpy restatement of the reference) on the host cores, on
+                 the bounded sample REF_SAMPLE_BATCH rows per step (rank 0, N=1 only)
+Extra objects in the same JSON line (every one measured in this run):
+  strong_scaling : BASELINE.json configs[4] -- the same model at a FIXED global batch of 65536
+                   (65536/N rows per GPU): ms/step and samples/s; efficiency = T(1) / (N T(N))
+  allreduce      : (N>1) the 268.5 MB gradient all-reduce timed alone -> bus bandwidth
+  checks         : (N>1) replicas' parameter checksums agree after the timed steps; the step-0
+                   loss equals ln(B_global * C) to the tolerance random init allows
+  mnist          : (N=1) BASELINE.json configs[0], the examples/mnist MLP at batch 128: the
+                   unmodified five-line loop (eager) and Model.train_step (recorded step)
 
-import numpy as np
+--impl reference times the CPU implementation alone (all host threads, also under torchrun), on
+the same config/metric/unit; each of its steps is a bounded sample of the workload: a train step
+on REF_SAMPLE_BATCH = 1024 of the 8192 rows (a full-batch reference step takes ~1 min: float64,
+4x re-walked backward).  The sample size is fixed -- it does not depend on --steps -- and is the
+same one `cpu_baseline` uses, so there is ONE CPU figure per box.
+"""
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import math  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDE = dict(name="wide_mlp_4x4096", widths=[4096, 4096, 4096, 4096], d_in=4096, batch=8192)
 MNIST = dict(name="mnist_mlp_784-200-100-70-30-10", widths=[200, 100, 70, 30, 10], d_in=784, batch=128)
+REF_SAMPLE_BATCH = 1024     # rows per CPU-reference step on the wide MLP (fixed; see module docstring)
+STRONG_GLOBAL_BATCH = 65536  # BASELINE.json configs[4]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,12 +131,14 @@ class ClockSampler(object):
 
 
 def make_config(cfg, batch_per_gpu, world):
-    """the `config` object both arms print: the workload the metric is quoted on"""
+    """the `config` object BOTH arms print, key for key: the workload the metric is quoted on, and
+    the bounded sample of it one CPU-reference step runs"""
     return {"workload": cfg["name"], "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
             "d_in": cfg["d_in"], "widths": cfg["widths"], "optimizer": "Adam(1e-3)",
             "parallelism": "dp%d" % world,
-            "l2": "per-step working set (parameters, activations, tf32 planes) far exceeds the 126 MB L2 "
-                  "for the wide MLP; no flush between steps"}
+            "cpu_reference_sample": "%d rows per step" % ref_sample_batch(cfg),
+            "l2": "per-step working set (parameters, activations, operand planes) far exceeds the "
+                  "126 MB L2 for the wide MLP; no flush between steps"}
 
 
 def gemm_flops_per_step(cfg, batch):
@@ -126,67 +151,66 @@ def gemm_flops_per_step(cfg, batch):
     return fl
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the numpy oracle on the host cores
 # ------------------------------------------------------------------------------------------------
-def _oracle_model(cfg, sample_batch, seed=0):
+def ref_sample_batch(cfg):
+    return min(cfg["batch"], REF_SAMPLE_BATCH)
+
+
+def cpu_reference_throughput(cfg, steps, warmup):
+    """train steps of the numpy restatement of the reference (oracle/ref_numpy.py: float64
+    gradients, per-path backward, flattened Adam) on ref_sample_batch(cfg) rows; returns
+    (samples/s, s/step, description).  The first step runs on float32 parameters, later ones on
+    float64 (the reference promotes them, model.py:59-61), so warmup >= 1 times the steady state."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_numpy as R
-    np.random.seed(seed)
-    rng = np.random.RandomState(seed)
+    sample = ref_sample_batch(cfg)
+    np.random.seed(0)
+    rng = np.random.RandomState(0)
     C = cfg["widths"][-1]
-    x = rng.rand(sample_batch, cfg["d_in"]).astype(np.float32)
-    labels = np.eye(C, dtype=np.float32)[rng.randint(0, C, sample_batch)]
+    x = rng.rand(sample, cfg["d_in"]).astype(np.float32)
+    labels = np.eye(C, dtype=np.float32)[rng.randint(0, C, sample)]
     mlp = R.RefMLP(cfg["widths"], R.RefAdam(lr=1e-3))
-    return mlp, x, labels
-
-
-def cpu_reference_throughput(cfg, sample_batch, steps, warmup):
-    mlp, x, labels = _oracle_model(cfg, sample_batch)
     for _ in range(warmup):
         mlp.train_step(x, labels)
     t0 = time.perf_counter()
     for _ in range(steps):
         mlp.train_step(x, labels)
-    dt = time.perf_counter() - t0
-    return sample_batch * steps / dt, dt / steps
-
-
-def pick_reference_sample(cfg, total_steps, budget_s=150.0):
-    """largest power-of-two sample batch (<= the config's batch) whose steps fit the time budget"""
-    probe = 32 if cfg["batch"] >= 32 else cfg["batch"]
-    mlp, x, labels = _oracle_model(cfg, probe)
-    mlp.train_step(x, labels)                    # float32 parameters
-    t0 = time.perf_counter()
-    mlp.train_step(x, labels)                    # float64 parameters from here on
-    t = time.perf_counter() - t0
-    b = probe
-    # step time grows (sub-)linearly with the batch; the optimiser part is batch independent
-    while b * 2 <= min(cfg["batch"], 1024) and t * 2 * total_steps <= budget_s:
-        b *= 2
-        t *= 2
-    return b
+    dt = (time.perf_counter() - t0) / steps
+    desc = ("%d timed train steps (after %d warm-up) of the %s on %d of its %d rows per step, "
+            "oracle/ref_numpy.py on %d host threads, %.2f s/step" % (
+                steps, warmup, cfg["name"], sample, cfg["batch"], host_cores(), dt))
+    return sample / dt, dt, desc
 
 
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = pick_reference_sample(cfg, args.steps + args.warmup)
-    value, s_per_step = cpu_reference_throughput(cfg, sample, args.steps, args.warmup)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    desc = "train steps of the %s at batch %d (numpy oracle, all host threads)" % (cfg["name"], sample)
+    steps = args.steps if args.steps_given else 10
+    value, s_per_step, desc = cpu_reference_throughput(cfg, steps, args.warmup)
+    note = None
+    if args.gpus > 1:
+        note = ("the reference has no data-parallel mode: this is the single-process CPU figure, "
+                "identical in meaning at every N (not a scaling point)")
     line = {
         "impl": "reference", "metric": "MLP train samples/sec", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(make_config(cfg, cfg["batch"], args.gpus), sample_batch=sample),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+        "config": make_config(cfg, cfg["batch"], args.gpus),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": host_cores(), "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if note:
+        line["note"] = note
     print(json.dumps(line))
 
 
@@ -208,16 +232,175 @@ def build_model(cfg):
     return net, Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=Adam(lr=1e-3))
 
 
+def synthetic_shard(cfg, B, rank, copies=2):
+    """`copies` synthetic batches of B rows for this rank: float32 inputs U[0,1), int labels"""
+    rng = np.random.RandomState(1000 + rank)
+    C = cfg["widths"][-1]
+    xs = [rng.rand(B, cfg["d_in"]).astype(np.float32) for _ in range(copies)]
+    ys = [rng.randint(0, C, B).astype(np.int32) for _ in range(copies)]
+    return xs, ys
+
+
+def one_hot_host(labels, C):
+    out = np.zeros((len(labels), C), np.float32)
+    out[np.arange(len(labels)), labels] = 1.0
+    return out
+
+
+class Stepper(object):
+    """the reference's five-line training loop body (run.py:79-83), or its recorded replay"""
+
+    def __init__(self, cfg, use_graph):
+        from core.losses import SoftmaxCrossEntropyLoss
+        np.random.seed(0)
+        self.net, self.model = build_model(cfg)
+        self.loss_layer = SoftmaxCrossEntropyLoss()
+        self.use_graph = use_graph
+
+    def __call__(self, x_t, y_t):
+        if self.use_graph:   # the same five calls, recorded once per batch shape and replayed
+            return self.model.train_step(x_t, y_t)
+        m = self.model
+        m.zero_grad()
+        pred = m.forward(x_t)
+        loss = self.loss_layer.loss(pred, y_t)
+        loss.backward()
+        m.step()
+        return loss
+
+    def param_checksum(self):
+        import core._backend as be
+        a = self.model._arena
+        if a is None:
+            return None
+        host = be.to_numpy(a["p"])
+        return float(np.sum(host.astype(np.float64))), float(np.sum(np.abs(host).astype(np.float64)))
+
+
+def timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm):
+    """(ms for `steps` steps, launches, gemm_ms, gemm_n, last loss) with device-resident inputs"""
+    import core._backend as be
+    import core._dist as dist
+    from core.tensor import Tensor
+    loss = None
+    for i in range(warmup):
+        loss = stepper(Tensor(x_dev[i % len(x_dev)]), Tensor(y_dev[i % len(y_dev)]))
+    if loss is not None:
+        float(loss.values)
+    dist.barrier()
+    if profile_gemm:
+        be.prof_enable(1)     # per-launch events around the tcgen05 GEMM (not recordable in a graph)
+    launches0 = be.launch_count()
+    ev0, ev1 = be.Event(), be.Event()
+    ev0.record()
+    for i in range(steps):
+        loss = stepper(Tensor(x_dev[i % len(x_dev)]), Tensor(y_dev[i % len(y_dev)]))
+    ev1.record()
+    dist.barrier()
+    ms = ev1.elapsed_ms_since(ev0)
+    launches = be.launch_count() - launches0
+    gemm_ms, gemm_n = (0.0, 0)
+    if profile_gemm:
+        gemm_ms, gemm_n = be.prof_collect()
+        be.prof_enable(0)
+    return ms, launches, gemm_ms, gemm_n, float(loss.values)
+
+
+def max_over_ranks(values):
+    import core._dist as dist
+    if dist.world_size() == 1:
+        return list(values)
+    import torch
+    import torch.distributed as td
+    t = torch.tensor(list(values), dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def gather_over_ranks(values):
+    import core._dist as dist
+    if dist.world_size() == 1:
+        return [list(values)]
+    import torch
+    import torch.distributed as td
+    t = torch.tensor(list(values), dtype=torch.float64)
+    out = [torch.zeros_like(t) for _ in range(dist.world_size())]
+    td.all_gather(out, t)
+    return [[float(v) for v in o] for o in out]
+
+
+def measure_strong(cfg, rank, world, steps=8, warmup=3):
+    """BASELINE.json configs[4]: global batch 65536 fixed, 65536/N rows on each GPU"""
+    import core._backend as be
+    if STRONG_GLOBAL_BATCH % world:
+        return None
+    B = STRONG_GLOBAL_BATCH // world
+    C = cfg["widths"][-1]
+    xs, ys = synthetic_shard(cfg, B, rank, copies=1)
+    x_dev = [be.from_numpy(xs[0])]
+    y_dev = [be.empty((B, C), be.F32)]
+    lab = be.from_numpy(ys[0].view(np.float32))
+    be.one_hot_into(y_dev[0], lab.ptr, B, C)
+    del xs
+    stepper = Stepper(cfg, use_graph=False)
+    ms, launches, _, _, last = timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm=False)
+    ms = max_over_ranks([ms])[0]
+    return {"config": "BASELINE.json configs[4]", "global_batch": STRONG_GLOBAL_BATCH,
+            "batch_per_gpu": B, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "value": STRONG_GLOBAL_BATCH * steps / (ms * 1e-3),
+            "unit": "samples/s", "final_loss": last,
+            "efficiency": "T(1) / (N * T(N)) over the ms_per_step of the N = 1, 2, 4, 8 lines"}
+
+
+def measure_allreduce(n_elems, reps=20):
+    """the gradient all-reduce alone: `reps` back-to-back in-place SUMs of an arena-sized vector"""
+    import core._backend as be
+    import core._dist as dist
+    world = dist.world_size()
+    buf = be.zeros((n_elems,), be.F32)
+    for _ in range(3):
+        dist.allreduce_sum(buf)
+    dist.barrier()
+    e0, e1 = be.Event(), be.Event()
+    e0.record()
+    for _ in range(reps):
+        dist.allreduce_sum(buf)
+    e1.record()
+    dist.barrier()
+    ms = max_over_ranks([e1.elapsed_ms_since(e0)])[0] / reps
+    nbytes = n_elems * 4
+    return {"bytes": nbytes, "ms": ms, "algbw_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9,
+            "reps": reps, "nvlink5_per_direction_gbs": 900.0}
+
+
+def measure_mnist(steps=2000, warmup=50):
+    """BASELINE.json configs[0] on one GPU: examples/mnist/run.py's network and loop at batch 128"""
+    import core._backend as be
+    cfg = dict(MNIST)
+    B, C = cfg["batch"], cfg["widths"][-1]
+    xs, ys = synthetic_shard(cfg, B, 0, copies=2)
+    x_dev = [be.from_numpy(x) for x in xs]
+    y_dev = [be.from_numpy(one_hot_host(y, C)) for y in ys]
+    out = {"config": "BASELINE.json configs[0]", "workload": cfg["name"], "batch": B}
+    for mode, use_graph in (("eager_five_line_loop", False), ("recorded_train_step", True)):
+        stepper = Stepper(cfg, use_graph)
+        ms, launches, _, _, last = timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm=False)
+        out[mode] = {"ms_per_step": ms / steps, "value": B * steps / (ms * 1e-3), "unit": "samples/s",
+                     "steps": steps, "launches_per_step": launches / steps, "final_loss": last}
+    return out
+
+
 def run_b200_arm(args, cfg):
     import core._backend as be
     import core._dist as dist
-    from core.losses import SoftmaxCrossEntropyLoss
     from core.tensor import Tensor
 
     dist.init_process_group()
     rank, world = dist.rank(), dist.world_size()
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torchrun)" % (args.gpus, world))
+    numa = dist.bind_to_local_numa_node()    # pinned staging buffers land next to this rank's GPU
     B = args.batch_per_gpu or cfg["batch"]
     if args.global_batch:
         lo, hi = dist.shard_bounds(args.global_batch, rank, world)
@@ -226,82 +409,68 @@ def run_b200_arm(args, cfg):
         B = hi - lo
     C = cfg["widths"][-1]
     peaks = read_peaks()
+    wide = args.workload == "wide"
 
     # synthetic inputs, one shard per rank; identical reference-style init on every rank
-    rng = np.random.RandomState(1000 + rank)
-    x_host = be.PinnedArray((2, B, cfg["d_in"]), np.float32)
-    y_host = be.PinnedArray((2, B, C), np.float32)
-    for k in range(2):
-        x_host.array[k] = rng.rand(B, cfg["d_in"]).astype(np.float32)
-        y_host.array[k] = 0.0
-        y_host.array[k][np.arange(B), rng.randint(0, C, B)] = 1.0
-    np.random.seed(0)
-    net, model = build_model(cfg)
-    loss_layer = SoftmaxCrossEntropyLoss()
-
-    x_dev = [be.from_numpy(x_host.array[k]) for k in range(2)]
-    y_dev = [be.from_numpy(y_host.array[k]) for k in range(2)]
-
+    xs, ys = synthetic_shard(cfg, B, rank, copies=2)
+    x_dev = [be.from_numpy(x) for x in xs]
+    y_dev = [be.from_numpy(one_hot_host(y, C)) for y in ys]
     use_graph = args.graph == "on" or (args.graph == "auto" and args.workload == "mnist")
+    stepper = Stepper(cfg, use_graph)
 
-    def train_step(x_t, y_t):
-        if use_graph:   # the same five calls, recorded once per batch shape and replayed
-            return model.train_step(x_t, y_t)
-        model.zero_grad()
-        pred = model.forward(x_t)
-        loss = loss_layer.loss(pred, y_t)
-        loss.backward()
-        model.step()
-        return loss
+    # ---- step-0 loss: with zero biases and Xavier weights the logits are O(1) and the global
+    # softmax is near uniform over B_global*C entries, so loss_0 = ln(B_global*C) up to the logit spread
+    loss0 = float(stepper(Tensor(x_dev[0]), Tensor(y_dev[0])).values)
+    expect0 = math.log(B * world * C)
+    checks = {"loss_step0": loss0, "ln_Bglobal_C": expect0, "loss_step0_ok": abs(loss0 - expect0) < 0.25}
+    if not checks["loss_step0_ok"]:
+        raise SystemExit("step-0 loss %.4f is not ln(B_global*C) = %.4f: the CE normaliser does not "
+                         "span the global batch" % (loss0, expect0))
 
     # ---- device-resident throughput ("value") --------------------------------------------------
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()                       # nvidia-smi needs ~0.3 s to produce its first sample
-    for i in range(args.warmup):
-        loss = train_step(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
-    float(loss.values)
-    dist.barrier()
+    for i in range(1, args.warmup):       # the step-0 check above was warm-up step 0
+        stepper(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
+    be.sync()
     s_first = sampler.mark()
-    if not use_graph:
-        be.prof_enable(1)     # per-launch events around the tcgen05 GEMM (not recordable in a graph)
-    launches0 = be.launch_count()
-    ev0, ev1 = be.Event(), be.Event()
-    ev0.record()
-    for i in range(args.steps):
-        loss = train_step(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
-    ev1.record()
-    dist.barrier()
-    ms = ev1.elapsed_ms_since(ev0)
+    ms, launches, gemm_ms, gemm_n, last_loss = timed_steps(stepper, x_dev, y_dev, args.steps, 0,
+                                                           profile_gemm=not use_graph)
     s_last = sampler.mark() + 1
-    launches = be.launch_count() - launches0
-    gemm_ms, gemm_n = be.prof_collect()
-    be.prof_enable(0)
     clocks = sampler.stop(s_first, s_last)
-    last_loss = float(loss.values)
+
+    # ---- replicas agree (driver-visible correctness at N>1) ------------------------------------
+    if world > 1:
+        sums = gather_over_ranks(stepper.param_checksum())
+        same = all(s == sums[0] for s in sums)
+        checks.update({"replica_param_checksums_equal": same, "param_sum": sums[0][0], "param_abs_sum": sums[0][1]})
+        if not same:
+            raise SystemExit("replicas diverged: parameter checksums %r" % (sums,))
 
     # ---- end to end from host buffers ("e2e"): the public input pipeline ----------------------
     # utils.data_iterator.PrefetchIterator over a host data set of 4 batches (pinned in place):
-    # batch i+1 is DMA'd on the copy stream while step i runs; the loss is read back every step.
+    # batch i+1 is DMA'd on the copy stream while step i runs; labels travel as int32 and the
+    # one-hot rows are built on the device; the loss is read back every step.
     from utils.data_iterator import PrefetchIterator
     n_host_batches = 4
     x_data = np.empty((n_host_batches * B, cfg["d_in"]), np.float32)
-    y_data = np.zeros((n_host_batches * B, C), np.float32)
+    y_data = np.empty((n_host_batches * B,), np.int32)
     for k in range(n_host_batches):
-        x_data[k * B:(k + 1) * B] = x_host.array[k % 2]
-        y_data[k * B:(k + 1) * B] = y_host.array[(k + 1) % 2]
-    del x_host, y_host
+        x_data[k * B:(k + 1) * B] = xs[k % 2]
+        y_data[k * B:(k + 1) * B] = ys[(k + 1) % 2]
+    del xs
     e2e_steps = args.steps
-    feed = iter(PrefetchIterator(batch_size=B, loop=True)(x_data, y_data))
+    feed = iter(PrefetchIterator(batch_size=B, loop=True, num_classes=C)(x_data, y_data))
     for _ in range(2):                                   # e2e warm-up
         batch = next(feed)
-        float(train_step(batch.inputs, batch.targets).values)
+        float(stepper(batch.inputs, batch.targets).values)
     dist.barrier()
     t0 = time.perf_counter()
     e0, e1 = be.Event(), be.Event()
     e0.record()
     batch = next(feed)
     for _ in range(e2e_steps):
-        loss = train_step(batch.inputs, batch.targets)   # queued; the GPU starts on it
+        loss = stepper(batch.inputs, batch.targets)      # queued; the GPU starts on it
         batch = next(feed)                               # H2D of a following batch is queued in here,
                                                          # while the GPU runs the step just queued
         float(loss.values)                               # D2H read of this step's loss
@@ -311,20 +480,14 @@ def run_b200_arm(args, cfg):
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e2e_ms, e2e_wall)
     feed.close()
+    del feed, x_data, y_data
 
-    # ---- max over ranks ------------------------------------------------------------------------
-    if world > 1:
-        import torch
-        import torch.distributed as td
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-
+    ms, e2e_ms = max_over_ranks([ms, e2e_ms])
     global_batch = B * world
     value = global_batch * args.steps / (ms * 1e-3)
     e2e_value = global_batch * e2e_steps / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 3xTF32 GEMM) ---------------------------------
+    # ---- roofline of the dominant kernel (tcgen05 split GEMM) ----------------------------------
     flops_step = gemm_flops_per_step(cfg, B)
     roofline = None
     if gemm_n:
@@ -350,14 +513,22 @@ def run_b200_arm(args, cfg):
                         peaks["source"], peaks["bf16_sustained"], int(cost),
                         "1 TF32 + 2 BF16 MMAs per algorithmic MMA" if mix else "3 TF32 MMAs per algorithmic MMA")}
 
+    # ---- the extra measurements ------------------------------------------------------------------
+    arena_elems = stepper.model._arena["p"].size if stepper.model._arena else 0
+    del stepper, x_dev, y_dev
+    strong = allred = mnist = None
+    if wide and not args.global_batch and not args.no_extras:
+        if world > 1 and arena_elems:
+            allred = measure_allreduce(arena_elems)
+        strong = measure_strong(cfg, rank, world)
+        if world == 1:
+            mnist = measure_mnist()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = 256 if cfg["batch"] >= 256 else cfg["batch"]
-        v, s_per = cpu_reference_throughput(cfg, sample, steps=2, warmup=0)
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-        cpu_baseline = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                        "sample": "2 train steps of the %s at batch %d with oracle/ref_numpy.py "
-                                  "(%.2f s/step)" % (cfg["name"], sample, s_per)}
+        v, s_per, desc = cpu_reference_throughput(cfg, steps=2, warmup=1)
+        cpu_baseline = {"value": v, "unit": "samples/s", "cores": host_cores(), "kind": "port",
+                        "sample": desc}
 
     if rank == 0:
         line = {
@@ -369,14 +540,18 @@ def run_b200_arm(args, cfg):
             "dtype": "f32 (tensor-core GEMMs: %s, fp32 accumulate)" % (
                 "tf32 main term + bf16 cross terms" if be.TC_SPLIT == "mix" else "3xTF32"),
             "data": "synthetic",
-            "config": dict(make_config(cfg, B, world),
-                           step_mode="cuda_graph_replay" if use_graph else "eager_launches"),
+            "config": make_config(cfg, B, world),
+            "step_mode": "cuda_graph_replay" if use_graph else "eager_launches",
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "samples/s",
-                    "h2d_bytes_per_step": int(B * (cfg["d_in"] + C) * 4), "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / e2e_steps},
+                    "h2d_bytes_per_step": int(B * cfg["d_in"] * 4 + B * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "pipeline": "PrefetchIterator: float32 inputs + int32 labels from pinned host "
+                                "memory on a copy stream, one-hot rows built on the device"},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": last_loss,
             "gemm_tflops_algorithmic": flops_step * args.steps / (ms * 1e-3) / 1e12,
+            "checks": checks, "numa": numa,
+            "strong_scaling": strong, "allreduce": allred, "mnist": mnist,
         }
         print(json.dumps(line))
     dist.destroy_process_group()
@@ -385,7 +560,7 @@ def run_b200_arm(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wide", choices=["wide", "mnist"])
@@ -397,7 +572,12 @@ def main():
                     help="replay the step as a CUDA graph (Model.train_step); auto = on for the "
                          "launch-bound mnist workload, off for the wide MLP")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the strong-scaling / all-reduce / mnist side measurements")
     args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 50
     args.warmup = max(args.warmup, 3)
     cfg = dict(WIDE if args.workload == "wide" else MNIST)
     if args.impl == "reference":

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
     "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
+    "tnn_one_hot": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "tnn_nccl_unique_id": [_c_vp],
@@ -644,6 +645,12 @@ def strided_copy(dst, dst_off, dst_strides, src, src_off, src_strides, shape):
     if _lib.tnn_strided_copy(_DT_CODE[dst.dtype], dst.ptr + dst_off * isz, src.ptr + src_off * isz,
                              len(shape), _i64arr(shape), _i64arr(dst_strides), _i64arr(src_strides)):
         _raise("tnn_strided_copy")
+
+
+def one_hot_into(out, labels_i32_ptr, n_rows, n_classes):
+    """out (n_rows, n_classes) <- one-hot rows of the int32 device vector at `labels_i32_ptr`"""
+    if _lib.tnn_one_hot(_DT_CODE[out.dtype], out.ptr, labels_i32_ptr, n_rows, n_classes):
+        _raise("tnn_one_hot")
 
 
 def gather_rows(x, idx_dev, n_idx):

@@ -51,6 +51,12 @@ class Model(object):
     def load(self, path):
         with open(path, "rb") as f:
             state = pickle.load(f)
+        if hasattr(state, "layers"):
+            # a checkpoint in the reference's format (model.py:18-21 pickles the whole Net): its
+            # tensors were unpickled without going through __init__ and carry the reference's
+            # attribute names -- take the arrays out of them
+            state = [{k: _pickled_values(v) for k, v in getattr(layer, "params", {}).items()
+                      if v is not None} for layer in state.layers]
         params = self.net.get_parameters()
         if len(state) != len(params):
             raise ValueError("Incompatible architecture: %d layers in the file, %d in the model"
@@ -66,6 +72,8 @@ class Model(object):
                     layer.params[k] = Tensor(arr, requires_grad=True, dtype=arr.dtype)
                     if hasattr(layer, "is_init"):
                         layer.is_init = True
+                    if hasattr(layer, "shapes") and k in layer.shapes:
+                        layer.shapes[k] = list(arr.shape)
                 else:
                     cur.values = arr
                     cur.zero_grad()
@@ -134,8 +142,25 @@ class Model(object):
     # ------------------------------------------------------------------ training step
     def step(self):
         plist = self._param_list()
-        fused = self._arena_valid(plist) or self._build_arena(plist)
-        if fused and all(p._grad is p._gslot for p in plist):
+        # the fused arena kernel implements the built-in update rules only: an optimiser whose class
+        # overrides the reference's extension points (_compute_step / compute_step) goes through
+        # compute_step(), consistently from its first step on (its state then has the reference's
+        # unpadded flat layout)
+        fused = self.optimizer.uses_builtin_rule() and (
+            self._arena_valid(plist) or self._build_arena(plist))
+        if fused:
+            for p in plist:
+                # a gradient that lives outside its arena slot (user code assigned `p.grad = ...`):
+                # bring it into the slot instead of leaving the fused path -- the optimiser state is
+                # laid out over the padded arena and cannot follow to the unpadded generic layout
+                if p._grad is not p._gslot:
+                    if p._grad is None:
+                        if not p._grad_zero:
+                            raise TypeError("a parameter has no gradient (call zero_grad() first)")
+                    else:
+                        be.copy_into(p._gslot, p._coerce_grad(p._grad))
+                        p._grad_zero = False
+                    p._grad, p._grad_host = p._gslot, None
             a = self._arena
             for p in plist:
                 if p._grad_zero:             # no gradient reached this parameter in this step
@@ -230,7 +255,19 @@ class Model(object):
         plist = self._param_list()
         if not (plist and self._arena_valid(plist)) or self.optimizer.opt_code is None:
             return None
-        step = _CapturedStep(self, x, y)
+        if not self.optimizer.uses_builtin_rule():
+            return None
+        try:
+            step = _CapturedStep(self, x, y)
+        except be.BackendError:
+            # something in the step cannot be recorded (a host read of a device value, an upload,
+            # scratch growth): the aborted recording ran nothing, so drop what it cached and let the
+            # caller run this batch -- and every later one of this shape -- eagerly
+            be.new_split_epoch()
+            for p in plist:
+                p._touch()
+            self.zero_grad()
+            return None
         if not self._arena_valid(plist):   # the recorded step left the fused path
             step.destroy()
             return None
@@ -247,6 +284,19 @@ class Model(object):
             return
         for p in plist:
             p.zero_grad()
+
+
+def _pickled_values(t):
+    """the ndarray inside a tensor that came out of pickle: this engine's Tensor, or the
+    reference's (attribute `_values`, tensor.py:20), or a bare array"""
+    if isinstance(t, np.ndarray):
+        return t
+    d = getattr(t, "__dict__", {})
+    if "_values" in d:
+        return np.asarray(d["_values"])
+    if "_data" in d or hasattr(t, "values"):
+        return np.asarray(t.values)
+    raise ValueError("unrecognised checkpoint entry of type %s" % type(t).__name__)
 
 
 class _CapturedStep(object):

@@ -7,7 +7,14 @@ the result is handed back per parameter.  Here the flat vector is a device buffe
 gradients in flat arenas, apply_fused() updates the parameters in place with that same kernel:
 read g, state, p and write state, p in one pass (28 B/param for Adam).
 
-As in the reference, weight_decay is accepted and not applied (optimizer.py:28-29).
+weight_decay: the reference accepts it and never applies it (the line that would,
+`_step -= self.weight_decay * v`, is commented out at optimizer.py:28-29).  Same here by default;
+setting `optimizer.apply_weight_decay = True` turns exactly that line on (fused path: inside the
+optimiser kernel, hyper-parameter slot 7; compute_step path: on the per-parameter step views).
+
+The fused arena path is only taken for the built-in update rules: an optimiser whose class
+overrides `_compute_step` or `compute_step` (the reference's extension point) always goes
+through compute_step(), see core.model.Model.step.
 """
 import numpy as np
 
@@ -26,6 +33,8 @@ class BaseOptimizer(object):
 
     opt_code = None
     n_state = 0
+
+    apply_weight_decay = False   # opt-in: the reference has the decay line commented out
 
     def __init__(self, lr, weight_decay):
         self.lr = lr
@@ -46,7 +55,14 @@ class BaseOptimizer(object):
             if g.size:
                 be.copy_into(flat.view((g.size,), p), be.astype(g, dt).view((g.size,)))
             p += g.size
-        flat_step = self._compute_step(flat)
+        # a user-defined _compute_step may hand back a numpy array (the reference's contract)
+        flat_step = _as_darray(self._compute_step(flat))
+        if flat_step.dtype != dt:
+            flat_step = be.astype(flat_step, dt)
+        if flat_step.size != total:
+            raise ValueError("_compute_step returned %d elements for %d gradients" % (flat_step.size, total))
+        flat_step = flat_step.view((total,))
+        wd = self._decay_coefficient()
 
         p = 0
         steps = []
@@ -54,10 +70,32 @@ class BaseOptimizer(object):
             layer = dict()
             for k, v in param.items():
                 block = int(np.prod(v.shape))
-                layer[k] = flat_step.view(tuple(v.shape), p)
+                step = flat_step.view(tuple(v.shape), p)
+                if wd:      # optimizer.py:28-29, opt-in
+                    vd = be.astype(_as_darray(v), dt)
+                    step = be.ew(be.SUB, step, be.ew(be.MUL, be.full((), wd, dt), vd))
+                layer[k] = step
                 p += block
             steps.append(layer)
         return steps
+
+    def uses_builtin_rule(self):
+        """True when the update is one of this module's fused kernels and nobody overrode the
+        reference's extension points (_compute_step / compute_step) in a subclass"""
+        cls = type(self)
+        return (self.opt_code is not None
+                and cls._compute_step is BaseOptimizer._compute_step
+                and cls.compute_step is BaseOptimizer.compute_step)
+
+    def _decay_coefficient(self):
+        return float(self.weight_decay) if (self.apply_weight_decay and self.weight_decay) else 0.0
+
+    def _hyper8(self):
+        """this step's kernel coefficients: the rule's own in slots 0-5, weight decay in slot 7"""
+        vals = list(self._hyper())
+        vals += [0.0] * (8 - len(vals))
+        vals[7] = self._decay_coefficient()
+        return vals
 
     def _compute_step(self, grad):
         """flat device gradient -> flat device step (optimizer.py:37-38)"""
@@ -73,7 +111,7 @@ class BaseOptimizer(object):
 
     def step_hyper(self):
         """this step's hyper-parameters (Adam: advances t); a captured step reads them from device"""
-        return self._hyper_dev if self._hyper_dev is not None else self._hyper()
+        return self._hyper_dev if self._hyper_dev is not None else self._hyper8()
 
     def apply_fused_range(self, param_flat, grad_flat, lo, hi, hyper):
         """the fused update on elements [lo, hi) of the flat arenas, with hyper from step_hyper()"""
@@ -101,16 +139,13 @@ class BaseOptimizer(object):
             raise ValueError("optimizer state was built for %d parameters of %s, got %d of %s"
                              % (self._state[0].size, self._state[0].dtype, grad.size, grad.dtype))
         s = self._state + [None, None]
-        hyper = self._hyper_dev if self._hyper_dev is not None else self._hyper()
+        hyper = self._hyper_dev if self._hyper_dev is not None else self._hyper8()
         be.opt_step(self.opt_code, param, step_out, grad, s[0], s[1], hyper)
 
     def upload_hyper(self, dst):
         """advance to the next step (Adam: t += 1) and put its coefficients into the 8-double device
         vector a captured step reads them from"""
-        h = np.zeros(8, dtype=np.float64)
-        vals = self._hyper()
-        h[:len(vals)] = vals
-        be.upload_into(dst, h)
+        be.upload_into(dst, np.asarray(self._hyper8(), dtype=np.float64))
 
     def _hyper(self):
         raise NotImplementedError

@@ -10,7 +10,10 @@ Differences from the reference that are deliberate:
   * a gradient has its tensor's dtype (the reference makes every gradient float64); float32
     parameters stay float32.  Python scalars adopt the dtype of the tensor they meet.
   * integer / bool inputs are stored as float64.
-  * .values and .grad return host copies (numpy arrays); writes go through the setters.
+  * .values and .grad return host copies (numpy arrays) marked READ-ONLY: the reference hands out
+    its live arrays (tensor.py:20,31-33), so `t.values[i] = v` or `p.grad *= 0.5` edit the tensor
+    there; here such an edit could not reach the device, so it raises instead of being lost.
+    Writes go through the setters (`t.values = ...`, `p.grad = ...`).
 """
 import numpy as np
 
@@ -18,6 +21,11 @@ import core._backend as be
 import core.ops as ops
 
 _SCALAR_TYPES = (int, float, bool, np.integer, np.floating, np.bool_)
+
+
+def _readonly(arr):
+    arr.setflags(write=False)
+    return arr
 
 
 def as_tensor(obj, like=None):
@@ -59,7 +67,7 @@ class Tensor(object):
     def values(self):
         """host copy of the tensor (numpy array); one D2H transfer, cached until storage changes"""
         if self._host is None:
-            self._host = be.to_numpy(self._data)
+            self._host = _readonly(be.to_numpy(self._data))
         return self._host
 
     @values.setter
@@ -89,12 +97,12 @@ class Tensor(object):
         """host copy of the accumulated gradient, or None (tensor.py:22)"""
         if self._grad_zero:      # zeroed and nothing accumulated since (an arena slot is not
             if self._grad_host is None:   # cleared until something is written or the step needs it)
-                self._grad_host = np.zeros(self.shape, dtype=self._data.dtype)
+                self._grad_host = _readonly(np.zeros(self.shape, dtype=self._data.dtype))
             return self._grad_host
         if self._grad is None:
             return None
         if self._grad_host is None:
-            self._grad_host = be.to_numpy(self._grad)
+            self._grad_host = _readonly(be.to_numpy(self._grad))
         return self._grad_host
 
     @grad.setter

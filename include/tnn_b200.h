@@ -166,6 +166,10 @@ int tnn_scatter_rows(int dtype, void* out, const void* g, const int64_t* idx_dev
 /* arbitrary numpy key, flattened: out[i] = x[flat_idx[i]] / out[flat_idx[i]] = g[i] */
 int tnn_gather_flat(int dtype, void* out, const void* x, const int64_t* idx_dev, int64_t n);
 int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev, int64_t n);
+/* dense one-hot label rows built on the device from int32 class labels: the `np.eye(C)[targets]`
+ * of examples/mnist/run.py:27-28 (get_one_hot) without shipping B*C floats over PCIe.
+ * out[r, c] = (labels[r] == c), out is (B, C) contiguous in `dtype` */
+int tnn_one_hot(int dtype, void* out, const int32_t* labels_dev, int64_t B, int64_t C);
 
 /* ---- GEMM (ops.py:150-163 dot_: A@B, grad@B.T, A.T@grad) ----------------------------------- */
 /* SIMT path, any shape, f32/f64.  C[M,N] (ldc) = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C).
@@ -268,7 +272,9 @@ int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, i
  * param += step).  s0/s1 are the optimizer state vectors (Adam m,v; RMSProp ms,mom; ...), h[] the
  * hyper-parameters:
  *   SGD [lr]; ADAM [lr, b1, b2, eps, 1-b1^t, 1-b2^t]; RMSPROP [lr, decay, momentum, eps];
- *   MOMENTUM [lr, momentum]; ADAGRAD [lr, eps]; ADADELTA [lr, decay, eps].
+ *   MOMENTUM [lr, momentum]; ADAGRAD [lr, eps]; ADADELTA [lr, decay, eps];
+ *   every rule: h[7] = weight-decay coefficient, 0 = off (optimizer.py:28-29 `_step -= wd * v`,
+ *   commented out upstream and therefore opt-in here; needs param != NULL).
  * param (updated in place: param += step) and step_out (receives step) may each be NULL. */
 int tnn_opt_step(int opt, int dtype, void* param, void* step_out, const void* grad, void* s0,
                  void* s1, int64_t n, const double* h, int n_h);

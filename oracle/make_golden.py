@@ -11,6 +11,11 @@ Outputs (small, committed):
                                 70-30-10, Adam 1e-3, batch 128, np.random.seed(0), synthetic
                                 MNIST-shaped data) + first-step gradients' norms + final params'
                                 checksums
+  tests/golden/mnist_learn_traj.npz  the same loop on LEARNABLE synthetic data (oracle/ref_fp32.py
+                                learnable_mnist: class templates + noise): the loss falls by > 1
+                                over the 100 steps, so the 1e-4 trajectory bound discriminates
+  tests/golden/ref_checkpoint.pkl    a checkpoint in the reference's own format (pickled Net) +
+  tests/golden/ref_checkpoint_io.npz an input batch and the forward values it gives
   tests/golden/mlp_step.npz     3 Adam steps of a small wide-style MLP (4 x Dense(64), fp32
                                 one-hot labels): losses, first-step gradients, final parameters
 """
@@ -41,6 +46,7 @@ from utils.data_iterator import BatchIterator  # noqa: E402
 
 import op_cases  # noqa: E402
 import ref_numpy  # noqa: E402
+import ref_fp32  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -80,9 +86,12 @@ def gen_optimizers():
     print("optimizers.npz")
 
 
-def gen_mnist_traj():
+def gen_mnist_traj(learnable=False):
     np.random.seed(0)
-    x, y, onehot = ref_numpy.synthetic_mnist(12800, seed=0)
+    if learnable:
+        x, y, onehot = ref_fp32.learnable_mnist(12800, seed=0)
+    else:
+        x, y, onehot = ref_numpy.synthetic_mnist(12800, seed=0)
     train_x, train_y = Tensor(x), Tensor(onehot)
     net = Net([Dense(200), ReLU(), Dense(100), ReLU(), Dense(70), ReLU(), Dense(30), ReLU(), Dense(10)])
     model = Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=ref_opt.Adam(lr=1e-3))
@@ -102,9 +111,10 @@ def gen_mnist_traj():
         if len(losses) == 100:
             break
     sums = np.array([float(np.sum(p.values)) for layer in net.get_parameters() for p in layer.values()])
-    np.savez_compressed(os.path.join(OUT, "mnist_traj.npz"), losses=np.array(losses),
+    name = "mnist_learn_traj.npz" if learnable else "mnist_traj.npz"
+    np.savez_compressed(os.path.join(OUT, name), losses=np.array(losses),
                         first_grad_norms=first_grad_norms, final_param_sums=sums)
-    print("mnist_traj.npz: loss %.6f -> %.6f" % (losses[0], losses[-1]))
+    print("%s: loss %.6f -> %.6f" % (name, losses[0], losses[-1]))
 
 
 def gen_mlp_step():
@@ -140,8 +150,24 @@ def gen_mlp_step():
     print("mlp_step.npz: losses", losses)
 
 
+def gen_ref_checkpoint():
+    """a checkpoint written by the reference's own Model.save (model.py:18-21: the pickled Net),
+    and the forward values it must reproduce once loaded"""
+    np.random.seed(21)
+    x = np.random.rand(5, 4).astype(np.float32)
+    # the reference can only pickle a Net that has not run yet (after a forward the layers hold
+    # tensors whose closures do not pickle), so: eager initialisation, save, then forward
+    net = Net([Dense(3, num_in=4), ReLU(), Dense(2, num_in=3)])
+    model = Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=ref_opt.Adam(lr=1e-3))
+    model.save(os.path.join(OUT, "ref_checkpoint.pkl"))
+    y = model.forward(Tensor(x)).values
+    np.savez_compressed(os.path.join(OUT, "ref_checkpoint_io.npz"), x=x, y=np.array(y))
+
+
 if __name__ == "__main__":
     gen_ops()
     gen_optimizers()
     gen_mnist_traj()
+    gen_mnist_traj(learnable=True)
     gen_mlp_step()
+    gen_ref_checkpoint()

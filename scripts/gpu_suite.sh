@@ -34,11 +34,12 @@ for s in $STAGES; do
     graph) timeout 900 python -m pytest tests/test_gpu_graph.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_graph.log 2>&1 ;;
     mnist_ab) for g in on off on off; do timeout 300 python bench.py --workload mnist --steps 2000 --warmup 50 --graph $g --no-cpu-baseline >> gpurun_out/bench_mnist_graph_$g.log 2>&1; done ;;
     ncu_mnist_graph) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -s 400 -c 200 --csv --log-file gpurun_out/launches_mnist_graph.csv python bench.py --workload mnist --steps 20 --warmup 10 --graph on --no-cpu-baseline > gpurun_out/ncu_mnist_graph.log 2>&1 ;;
+    diag)  timeout 600 python scripts/diag_fp32_traj.py > gpurun_out/diag_fp32.jsonl 2>&1 ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt
 done
-for f in gpurun_out/smoke.log gpurun_out/gemm_bench_mix.jsonl gpurun_out/gemm_bench_tf32x3.jsonl gpurun_out/pytest_graph.log gpurun_out/pytest_all.log gpurun_out/bench_mnist_graph_on.log gpurun_out/bench_mnist_graph_off.log gpurun_out/ncu_mnist_graph.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/memcheck.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
+for f in gpurun_out/diag_fp32.jsonl gpurun_out/smoke.log gpurun_out/gemm_bench_mix.jsonl gpurun_out/gemm_bench_tf32x3.jsonl gpurun_out/pytest_graph.log gpurun_out/pytest_all.log gpurun_out/bench_mnist_graph_on.log gpurun_out/bench_mnist_graph_off.log gpurun_out/ncu_mnist_graph.log gpurun_out/pytest_ops.log gpurun_out/pytest_train.log gpurun_out/pytest_gemm.log gpurun_out/pytest_large.log gpurun_out/bench.log gpurun_out/bench_cg2.log gpurun_out/bench_mnist.log gpurun_out/sweep.err gpurun_out/ncu_list.log gpurun_out/ncu_gemm.log gpurun_out/memcheck.log gpurun_out/pytest_dist.log gpurun_out/bench_n1.log gpurun_out/bench_n2.log gpurun_out/bench_n4.log gpurun_out/bench_n8.log; do
   [ -f $f ] && { echo "== $f"; tail -n 6 $f; }
 done
 cat gpurun_out/stages.txt

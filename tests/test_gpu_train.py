@@ -26,9 +26,11 @@ def _build(widths, lr=1e-3):
     return net, Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=Adam(lr=lr)), SoftmaxCrossEntropyLoss()
 
 
-def _mnist_trajectory(param_dtype, steps=100):
+def _mnist_trajectory(param_dtype, steps=100, kind="mnist_traj"):
     """examples/mnist/run.py's loop (run.py:78-84) on synthetic MNIST-shaped data, np.random.seed(0).
+    kind = "mnist_traj" (random labels) or "mnist_learn_traj" (learnable class templates).
     Returns (losses, first-step gradient norms, final parameter sums)."""
+    import ref_fp32
     import core.initializer as I
     from core.layers import Dense, ReLU
     from core.losses import SoftmaxCrossEntropyLoss
@@ -48,7 +50,10 @@ def _mnist_trajectory(param_dtype, steps=100):
             return Tensor(self.init(shape), requires_grad=True, dtype=param_dtype)
 
     np.random.seed(0)
-    x, y, onehot = R.synthetic_mnist(12800, seed=0)
+    if kind == "mnist_traj":
+        x, y, onehot = R.synthetic_mnist(12800, seed=0)
+    else:
+        x, y, onehot = ref_fp32.learnable_mnist(12800, seed=0)
     train_x, train_y = Tensor(x.astype(param_dtype)), Tensor(onehot)
     widths = [200, 100, 70, 30, 10]
     layers = []
@@ -76,13 +81,14 @@ def _mnist_trajectory(param_dtype, steps=100):
     return np.array(losses), first_norms, sums
 
 
-def test_mnist_mlp_loss_trajectory_float64_engine(golden_dir):
-    """north_star: the loss trajectory over 100 steps within 1e-4 of the reference's.  The reference
-    is a float64 computation from its second step on, so the like-for-like run keeps
-    the engine's parameters in float64: every kernel on the path (SIMT GEMM, bias/ReLU, fused CE,
-    column sums, arena Adam) in its float64 instantiation.  Measured: <= 1e-7."""
-    gold = np.load(os.path.join(golden_dir, "mnist_traj.npz"))
-    losses, first_norms, sums = _mnist_trajectory(np.float64)
+@pytest.mark.parametrize("kind", ["mnist_traj", "mnist_learn_traj"])
+def test_mnist_mlp_loss_trajectory_float64_engine(golden_dir, kind):
+    """The reference is a float64 computation from its second step on; with the
+    engine's parameters kept in float64 every kernel on the path (SIMT GEMM, bias/ReLU, fused CE,
+    column sums, arena Adam) runs in its float64 instantiation and the 100-step trajectory agrees
+    to <= 1e-6 (measured <= 1e-7)."""
+    gold = np.load(os.path.join(golden_dir, kind + ".npz"))
+    losses, first_norms, sums = _mnist_trajectory(np.float64, kind=kind)
     assert np.max(np.abs(losses - gold["losses"])) <= 1e-6
     assert np.allclose(first_norms, gold["first_grad_norms"], rtol=1e-5, atol=1e-12)
     # parameter sums: Adam's first steps are +-lr on entries whose gradient is ~eps, so a 1e-12
@@ -90,24 +96,24 @@ def test_mnist_mlp_loss_trajectory_float64_engine(golden_dir):
     assert np.allclose(sums, gold["final_param_sums"], rtol=1e-4, atol=1e-4)
 
 
-def test_mnist_mlp_loss_trajectory_float32_engine(golden_dir):
-    """The same loop with float32 parameters (the production path).  Single precision cannot hold
-    1e-4 for 100 free-running steps on this data: a rounding-level difference flips a near-zero
-    ReLU pre-activation around step 7 and the Adam dynamics (sign-like steps of size lr) amplify
-    it -- a pure-numpy float32 restatement of the reference drifts to the same 1.4e-2.  So: tight
-    agreement while the trajectories are still the same trajectory, bounded drift afterwards."""
-    gold = np.load(os.path.join(golden_dir, "mnist_traj.npz"))
-    losses, first_norms, _ = _mnist_trajectory(np.float32)
+@pytest.mark.parametrize("kind", ["mnist_traj", "mnist_learn_traj"])
+def test_mnist_mlp_loss_trajectory_float32_engine(golden_dir, kind):
+    """north_star: "the loss trajectory over 100 steps within 1e-4" on the PRODUCTION path: float32
+    parameters, gradients and Adam state, free running for all 100 steps, against the trajectory
+    the real reference recorded (random-label data, where the loss stays near ln(B*C), and
+    learnable data, where it falls from 7.13 to 4.87).  oracle/ref_fp32.py shows plain single
+    precision holds 2e-6 here (tests/test_oracle_golden.py), so 1e-4 is asserted over every step."""
+    gold = np.load(os.path.join(golden_dir, kind + ".npz"))
+    losses, first_norms, _ = _mnist_trajectory(np.float32, kind=kind)
     diff = np.abs(losses - gold["losses"])
-    assert np.max(diff[:5]) <= 1e-5
-    assert np.max(diff) <= 5e-2
-    assert np.allclose(first_norms, gold["first_grad_norms"], rtol=1e-4, atol=1e-9)
+    assert np.max(diff) <= 1e-4, (int(np.argmax(diff)), float(np.max(diff)))
+    assert np.allclose(first_norms, gold["first_grad_norms"], rtol=1e-5, atol=1e-9)
 
 
 def test_mnist_mlp_teacher_forced_float32(golden_dir):
     """float32 engine vs oracle with the oracle's parameters loaded every step:
-    loss within 1e-5 and every gradient within rel 1e-4 at each of 20 steps, so errors cannot
-    compound."""
+    loss within 1e-5 and every gradient within rel 1e-5 (north_star's per-op bound) at each of 20
+    steps, so errors cannot compound."""
     from core.losses import SoftmaxCrossEntropyLoss
     from core.tensor import Tensor
     np.random.seed(0)
@@ -129,9 +135,12 @@ def test_mnist_mlp_teacher_forced_float32(golden_dir):
         loss = loss_layer.loss(model.forward(Tensor(xb)), Tensor(yb))
         loss.backward()
         assert abs(float(loss.values) - float(rloss.values)) <= 1e-5, it
-        for p, rp in zip(params, mlp.params()):
-            assert op_cases.rel_err(p.grad, rp.grad) <= 1e-4, it
+        for k, (p, rp) in enumerate(zip(params, mlp.params())):
+            assert op_cases.rel_err(p.grad, rp.grad) <= 1e-5, (it, k)
         mlp.step()
+        # both sides start the next step from bit-identical parameters
+        for rp in mlp.params():
+            rp.assign(rp.values.astype(np.float32).astype(np.float64))
 
 
 def test_wide_style_mlp_steps(golden_dir):

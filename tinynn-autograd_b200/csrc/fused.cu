@@ -487,8 +487,15 @@ opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH h
       s0[i] = Eg;
       s1[i] = delta;
     }
+    if (param) {
+      // optimizer.py:28-29 (`_step -= self.weight_decay * v`, commented out upstream): applied only
+      // when the host passes a non-zero coefficient in h[7] (BaseOptimizer.apply_weight_decay)
+      const T wd = (T)hh.h[7];
+      const T p = param[i];
+      if (wd != T(0)) step -= wd * p;
+      param[i] = p + step;
+    }
     if (step_out) step_out[i] = step;
-    if (param) param[i] += step;
   }
 }
 
@@ -502,6 +509,7 @@ adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh, cons
   constexpr int W = V4<T>::W;
   const T lr = (T)hh.h[0], omb1 = (T)(1.0 - hh.h[1]), omb2 = (T)(1.0 - hh.h[2]), eps = (T)hh.h[3];
   const T bc1 = (T)hh.h[4], bc2 = (T)hh.h[5];
+  const T wd = (T)hh.h[7];   // weight decay, 0 = off (optimizer.py:28-29)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
     U g, m, v, p;
@@ -514,7 +522,9 @@ adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh, cons
       m.e[k] += omb1 * (g.e[k] - m.e[k]);
       v.e[k] += omb2 * (g.e[k] * g.e[k] - v.e[k]);
       T mh = m.e[k] / bc1, vh = v.e[k] / bc2;
-      p.e[k] += -lr * mh / (m_sqrt(vh) + eps);
+      T step = -lr * mh / (m_sqrt(vh) + eps);
+      if (wd != T(0)) step -= wd * p.e[k];
+      p.e[k] += step;
     }
     reinterpret_cast<VT*>(s0)[i] = m.v;
     reinterpret_cast<VT*>(s1)[i] = v.v;

@@ -136,6 +136,33 @@ static int strided_copy_impl(T* dst, const T* src, int ndim, const int64_t* shap
   return 0;
 }
 
+// dense one-hot rows from integer class labels (examples/mnist/run.py:27-28 get_one_hot, done on
+// the device so a host-fed batch ships 4 B per sample instead of 4*C): out[r, c] = (labels[r] == c).
+// A label outside [0, C) gives an all-zero row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+one_hot_kernel(T* out, const int32_t* labels, int64_t B, int64_t C) {
+  const int64_t n = B * C;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / C;
+    out[i] = (int64_t)labels[r] == i - r * C ? T(1) : T(0);
+  }
+}
+
+// float32 rows whose length is a multiple of 4: one 128-bit store per thread
+__global__ void __launch_bounds__(256)
+one_hot_vec_kernel(float4* out, const int32_t* labels, int64_t B, int64_t C4) {
+  const int64_t n = B * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / C4;
+    const int64_t c = (i - r * C4) * 4;
+    const int64_t d = (int64_t)labels[r] - c;
+    out[i] = make_float4(d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f, d == 3 ? 1.f : 0.f);
+  }
+}
+
 }  // namespace tnn
 
 using namespace tnn;
@@ -213,6 +240,23 @@ int tnn_gather_flat(int dtype, void* out, const void* x, const int64_t* idx_dev,
 
 int tnn_scatter_flat(int dtype, void* out, const void* g, const int64_t* idx_dev, int64_t n) {
   return flat_common(false, dtype, out, g, idx_dev, n);
+}
+
+int tnn_one_hot(int dtype, void* out, const int32_t* labels_dev, int64_t B, int64_t C) {
+  TNN_REQUIRE_INIT();
+  if (B <= 0 || C <= 0) return 0;
+  cudaStream_t st = ctx().stream;
+  if (dtype == TNN_F32 && C % 4 == 0 && ((uintptr_t)out & 15) == 0) {
+    one_hot_vec_kernel<<<ew_grid(B * (C / 4), 256), 256, 0, st>>>((float4*)out, labels_dev, B, C / 4);
+  } else if (dtype == TNN_F32) {
+    one_hot_kernel<float><<<ew_grid(B * C, 256), 256, 0, st>>>((float*)out, labels_dev, B, C);
+  } else if (dtype == TNN_F64) {
+    one_hot_kernel<double><<<ew_grid(B * C, 256), 256, 0, st>>>((double*)out, labels_dev, B, C);
+  } else {
+    TNN_FAIL("tnn_one_hot: bad dtype");
+  }
+  TNN_POST_LAUNCH();
+  return 0;
 }
 
 }  // extern "C"

@@ -55,24 +55,34 @@ class PrefetchIterator(BaseIterator):
     straight out of it; with shuffling the rows of a batch are first gathered into a pinned staging
     buffer.  Two device buffers per stream of data: a buffer is rewritten two iterations later,
     after the compute stream has passed the kernels that read it.  loop=True wraps around
-    indefinitely (the caller breaks)."""
+    indefinitely (the caller breaks).
 
-    def __init__(self, batch_size=32, shuffle=False, loop=False):
+    num_classes=C: `targets` is the integer class-label vector (n,) a data set stores; 4 bytes per
+    sample cross PCIe and the dense one-hot rows the loss takes (run.py:27-28 get_one_hot) are
+    written on the device (tnn_one_hot) -- for the 4096-class wide MLP that halves the H2D bytes."""
+
+    def __init__(self, batch_size=32, shuffle=False, loop=False, num_classes=None):
         self.batch_size = batch_size
         self.shuffle = shuffle
         self.loop = loop
+        self.num_classes = num_classes
         self._cache = None
 
     def _buffers(self, inputs, targets):
         import core._backend as be
-        key = (id(inputs), id(targets), self.batch_size, self.shuffle)
+        key = (id(inputs), id(targets), self.batch_size, self.shuffle, self.num_classes)
         if self._cache is not None and self._cache["key"] == key:
             return self._cache
         xs = (self.batch_size,) + tuple(inputs.shape[1:])
         ys = (self.batch_size,) + tuple(targets.shape[1:])
+        t_dt = np.float32 if self.num_classes is None else np.int32
         cache = {"key": key, "dev": [(be.empty(xs, be.F32), be.empty(ys, be.F32)) for _ in range(2)]}
+        if self.num_classes is not None:
+            # int32 labels travel in a float32-sized device vector (same 4-byte elements); the
+            # one-hot rows are written next to them on the device
+            cache["onehot"] = [be.empty((self.batch_size, self.num_classes), be.F32) for _ in range(2)]
         if self.shuffle:
-            cache["stage"] = [(be.PinnedArray(xs, np.float32), be.PinnedArray(ys, np.float32))
+            cache["stage"] = [(be.PinnedArray(xs, np.float32), be.PinnedArray(ys, t_dt))
                               for _ in range(2)]
         else:
             cache["pinned"] = (be.RegisteredHostArray(inputs), be.RegisteredHostArray(targets))
@@ -83,7 +93,12 @@ class PrefetchIterator(BaseIterator):
         import core._backend as be
         from core.tensor import Tensor
         inputs = np.require(inputs, np.float32, "C")
-        targets = np.require(targets, np.float32, "C")
+        if self.num_classes is None:
+            targets = np.require(targets, np.float32, "C")
+        else:
+            if np.ndim(targets) != 1:
+                raise ValueError("num_classes is set: targets must be the 1-D integer label vector")
+            targets = np.require(targets, np.int32, "C")
         n_rows = len(inputs)
         bounds = _batch_bounds(n_rows, self.batch_size)
         if not bounds:
@@ -119,6 +134,11 @@ class PrefetchIterator(BaseIterator):
             last = (not self.loop) and step + 1 >= len(bounds)
             if not last:
                 pending = stage(step + 1)            # overlaps with the caller's work on this batch
+            if self.num_classes is not None:
+                n = xv.shape[0]
+                oh = buf["onehot"][step % 2].view((n, self.num_classes))
+                be.one_hot_into(oh, yv.ptr, n, self.num_classes)      # compute stream, after the copy
+                yv = oh
             yield Batch(inputs=Tensor(xv), targets=Tensor(yv))
             if last:
                 return
