@@ -42,6 +42,7 @@ if "--impl" in sys.argv and "reference" in sys.argv:
         os.environ.pop(_v, None)
 
 import argparse  # noqa: E402
+import gc  # noqa: E402
 import json  # noqa: E402
 import math  # noqa: E402
 import subprocess  # noqa: E402
@@ -277,6 +278,9 @@ class Stepper(object):
         return float(np.sum(host.astype(np.float64))), float(np.sum(np.abs(host).astype(np.float64)))
 
 
+LAST_TIMED_REGION = {}   # host-side facts about the most recent timed loop (diagnostics)
+
+
 def timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm):
     """(ms for `steps` steps, launches, gemm_ms, gemm_n, last loss) with device-resident inputs"""
     import core._backend as be
@@ -291,14 +295,21 @@ def timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm):
     if profile_gemm:
         be.prof_enable(1)     # per-launch events around the tcgen05 GEMM (not recordable in a graph)
     launches0 = be.launch_count()
+    mallocs0 = be.pool_stats()["cuda_mallocs"]
+    gc0 = [g["collections"] for g in gc.get_stats()]
     ev0, ev1 = be.Event(), be.Event()
+    t_host = time.perf_counter()
     ev0.record()
     for i in range(steps):
         loss = stepper(Tensor(x_dev[i % len(x_dev)]), Tensor(y_dev[i % len(y_dev)]))
     ev1.record()
+    host_ms = (time.perf_counter() - t_host) * 1e3
     dist.barrier()
     ms = ev1.elapsed_ms_since(ev0)
     launches = be.launch_count() - launches0
+    LAST_TIMED_REGION.update(
+        host_enqueue_ms=host_ms, cuda_mallocs=be.pool_stats()["cuda_mallocs"] - mallocs0,
+        gc_collections=[g["collections"] - a for g, a in zip(gc.get_stats(), gc0)])
     gemm_ms, gemm_n = (0.0, 0)
     if profile_gemm:
         gemm_ms, gemm_n = be.prof_collect()
@@ -430,14 +441,18 @@ def run_b200_arm(args, cfg):
     # ---- device-resident throughput ("value") --------------------------------------------------
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()                       # nvidia-smi needs ~0.3 s to produce its first sample
+    loss = None
     for i in range(1, args.warmup):       # the step-0 check above was warm-up step 0
-        stepper(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
+        # (bound to a name like in the timed loop: step i's graph then lives until step i+1 has
+        # produced its loss, so the pool reaches its steady-state footprint during warm-up)
+        loss = stepper(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
     be.sync()
     s_first = sampler.mark()
     ms, launches, gemm_ms, gemm_n, last_loss = timed_steps(stepper, x_dev, y_dev, args.steps, 0,
                                                            profile_gemm=not use_graph)
     s_last = sampler.mark() + 1
     clocks = sampler.stop(s_first, s_last)
+    timed_region = dict(LAST_TIMED_REGION)
 
     # ---- replicas agree (driver-visible correctness at N>1) ------------------------------------
     if world > 1:
@@ -550,7 +565,7 @@ def run_b200_arm(args, cfg):
                                 "memory on a copy stream, one-hot rows built on the device"},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": last_loss,
             "gemm_tflops_algorithmic": flops_step * args.steps / (ms * 1e-3) / 1e12,
-            "checks": checks, "numa": numa,
+            "checks": checks, "numa": numa, "timed_region": timed_region,
             "strong_scaling": strong, "allreduce": allred, "mnist": mnist,
         }
         print(json.dumps(line))

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
     "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
+    "tnn_set_gemm_reserved_sms": [_c_int],
     "tnn_one_hot": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
@@ -198,6 +199,13 @@ def device_info():
         _raise("tnn_device_info")
     return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "total_mem": tot.value,
             "l2_bytes": l2.value}
+
+
+def set_gemm_reserved_sms(n):
+    """SMs the persistent tcgen05 GEMM grid leaves free (for an NCCL kernel on the comm stream)"""
+    init()
+    if _lib.tnn_set_gemm_reserved_sms(int(n)):
+        _raise("tnn_set_gemm_reserved_sms")
 
 
 def pool_stats():

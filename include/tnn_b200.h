@@ -235,6 +235,10 @@ int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);
+/* The persistent tcgen05 grid leaves `n` SMs unoccupied (0..64, default 0): room for a collective
+ * kernel on another stream to run beside the backward pass (the per-layer gradient all-reduce of
+ * core/_dist.py).  Also settable with TNN_GEMM_RESERVED_SMS. */
+int tnn_set_gemm_reserved_sms(int n);
 /* Ordered split-K of the tcgen05 kernel: 0 = automatic (only the tiles of a ragged last wave are
  * cut along K, e.g. the 4096x4096x8192 dW products: 256 tiles on 74 CTA pairs), 1 = off, 2 / 4 =
  * every tile.  The K ranges of a tile are added in a fixed order, so results are deterministic.

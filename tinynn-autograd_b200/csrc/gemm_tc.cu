@@ -52,16 +52,30 @@ constexpr int UMMA_N = 256;               // accumulator columns per tile
 constexpr int UMMA_K = 8;                 // tf32
 constexpr int PLANE_ROW_BYTES = BK * 4;   // 128
 constexpr int NUM_THREADS = 384;         // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1-2: epilogue
-constexpr int CHUNK_KB = 4;               // K blocks accumulated inside the tensor core per chunk
+#ifndef TNN_CHUNK_KB
+#define TNN_CHUNK_KB 4
+#endif
+constexpr int CHUNK_KB = TNN_CHUNK_KB;    // K blocks accumulated inside the tensor core per chunk
 constexpr uint32_t TMEM_COLS = 512;
 
 template <int CG>
 struct Cfg {
   static constexpr int ROWS_B = UMMA_N / CG;                      // B rows staged per CTA
-  static constexpr int STAGES = CG == 1 ? 2 : 3;
   static constexpr int A_BYTES = ROWS_A * PLANE_ROW_BYTES;        // one plane
   static constexpr int B_BYTES = ROWS_B * PLANE_ROW_BYTES;
+#ifdef TNN_EXP48
+  // TIMING EXPERIMENT (separate library, never shipped as the product): stages hold hi + l16 only
+  // (the bf16(x) planes alias l16: wrong numerics), 48 KB instead of 64 KB, one stage more
+  static constexpr int STAGES = CG == 1 ? 3 : 4;
+  static constexpr int STAGE_BYTES = (3 * A_BYTES + 3 * B_BYTES) / 2;
+  static constexpr int A_PLANES_BYTES = A_BYTES + A_BYTES / 2;
+  static constexpr int L16_OFF_A = 0, L16_OFF_B = 0;
+#else
+  static constexpr int STAGES = CG == 1 ? 2 : 3;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo of both operands
+  static constexpr int A_PLANES_BYTES = 2 * A_BYTES;
+  static constexpr int L16_OFF_A = A_BYTES / 2, L16_OFF_B = B_BYTES / 2;
+#endif
   static constexpr int TILE_M = ROWS_A * CG;
   static constexpr int EPI_PATCH_BYTES = 8 * 4096;                // one 32x32 fp32 patch per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_PATCH_BYTES;
@@ -415,10 +429,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sa_lo = sa_hi + C::A_BYTES;
-          const uint32_t sb_hi = sa_lo + C::A_BYTES;
+          const uint32_t sb_hi = sa_hi + C::A_PLANES_BYTES;
           const uint32_t sb_lo = sb_hi + C::B_BYTES;
+          // (flags & 64: timing experiment only -- the bf16(x) planes are not fetched, results are wrong)
+#ifdef TNN_EXP48
+          const bool exp_skip_h16 = true;
           if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)C::STAGE_BYTES * CG);
+#else
+          const bool exp_skip_h16 = MIX && (flags & 64);
+          if (leader)
+            mbar_expect_tx(full_bar(stage), (uint32_t)(C::STAGE_BYTES - (exp_skip_h16 ? (C::A_BYTES + C::B_BYTES) / 2 : 0)) * CG);
+#endif
           const int k0 = kb * BK;
+          if (flags & 128) {
+            // timing experiment: no operand fetch at all (the MMAs run on whatever the stage holds);
+            // the transaction count armed above is satisfied by hand
+            if (leader) {
+#ifdef TNN_EXP48
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)), "r"((uint32_t)C::STAGE_BYTES * CG) : "memory");
+#else
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)),
+                           "r"((uint32_t)(C::STAGE_BYTES - (exp_skip_h16 ? (C::A_BYTES + C::B_BYTES) / 2 : 0)) * CG) : "memory");
+#endif
+            }
+          } else
           if constexpr (!MIX) {
             if constexpr (A_MN) {
 #pragma unroll
@@ -442,20 +476,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             }
           } else {
             // the second 32-bit plane's space holds the two bf16 planes
-            const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::A_BYTES / 2;
-            const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::B_BYTES / 2;
+            const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::L16_OFF_A;
+            const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::L16_OFF_B;
             if constexpr (A_MN) {
 #pragma unroll
               for (int j = 0; j < ROWS_A / 32; ++j)
                 tma_load_2d<CG>(sa_hi + j * MN_BOX_BYTES, &map_a_hi, full_bar(stage), row_a + 32 * j, k0);
 #pragma unroll
               for (int j = 0; j < ROWS_A / 64; ++j) {
-                tma_load_2d<CG>(sa_h16 + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 64 * j, k0);
+                if (!exp_skip_h16) tma_load_2d<CG>(sa_h16 + j * MN_BOX_BYTES, &map_a_lo, full_bar(stage), row_a + 64 * j, k0);
                 tma_load_2d<CG>(sa_l16 + j * MN_BOX_BYTES, &map_a_l16, full_bar(stage), row_a + 64 * j, k0);
               }
             } else {
               tma_load_2d<CG>(sa_hi, &map_a_hi, full_bar(stage), k0, row_a);
-              tma_load_2d<CG>(sa_h16, &map_a_lo, full_bar(stage), k0, row_a);
+              if (!exp_skip_h16) tma_load_2d<CG>(sa_h16, &map_a_lo, full_bar(stage), k0, row_a);
               tma_load_2d<CG>(sa_l16, &map_a_l16, full_bar(stage), k0, row_a);
             }
             if constexpr (B_MN) {
@@ -464,12 +498,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 tma_load_2d<CG>(sb_hi + j * MN_BOX_BYTES, &map_b_hi, full_bar(stage), row_b + 32 * j, k0);
 #pragma unroll
               for (int j = 0; j < C::ROWS_B / 64; ++j) {
-                tma_load_2d<CG>(sb_h16 + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 64 * j, k0);
+                if (!exp_skip_h16) tma_load_2d<CG>(sb_h16 + j * MN_BOX_BYTES, &map_b_lo, full_bar(stage), row_b + 64 * j, k0);
                 tma_load_2d<CG>(sb_l16 + j * MN_BOX_BYTES, &map_b_l16, full_bar(stage), row_b + 64 * j, k0);
               }
             } else {
               tma_load_2d<CG>(sb_hi, &map_b_hi, full_bar(stage), k0, row_b);
-              tma_load_2d<CG>(sb_h16, &map_b_lo, full_bar(stage), k0, row_b);
+              if (!exp_skip_h16) tma_load_2d<CG>(sb_h16, &map_b_lo, full_bar(stage), k0, row_b);
               tma_load_2d<CG>(sb_l16, &map_b_l16, full_bar(stage), k0, row_b);
             }
           }
@@ -504,8 +538,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             tc_fence_after();
             const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
             const uint32_t sa_lo = sa_hi + C::A_BYTES;
-            const uint32_t sb_hi = sa_lo + C::A_BYTES;
+            const uint32_t sb_hi = sa_hi + C::A_PLANES_BYTES;
             const uint32_t sb_lo = sb_hi + C::B_BYTES;
+            if (flags & 256) {
+              // timing experiment: operands are fetched but no MMA is issued
+            } else
             if constexpr (!MIX) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -522,8 +559,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 umma_tf32<CG>(tmem_d, da_hi, db_hi, idesc, 1u);
               }
             } else {
-              const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::A_BYTES / 2;
-              const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::B_BYTES / 2;
+              const uint32_t sa_h16 = sa_lo, sa_l16 = sa_lo + C::L16_OFF_A;
+              const uint32_t sb_h16 = sb_lo, sb_l16 = sb_lo + C::L16_OFF_B;
               // cross terms on the bf16 planes (small terms first): two K=16 steps
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -590,13 +627,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
                                (uint32_t)(acc * UMMA_N + half * 128);
+        if (!(flags & 512)) {     // (512: timing experiment, accumulator chunks are not drained)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(r[j]);
+          }
         }
         // this warp is done reading the accumulator: hand it back to the MMA issuer
         tc_fence_before();
@@ -951,6 +990,8 @@ static int g_group_m = 1;                      // tile rasterisation group; meas
 static int g_force_ksplit = 0;                 // 0 = auto (tail split), 1 = off, 2/4 = every tile (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3][2][2][2] = {};
+static int g_reserved_sms = 0;   // SMs the persistent grid leaves to other streams (NCCL)
+static int g_exp_flags = 0;  // timing experiments (TNN_EXP_*): OR-ed into the kernel's flags
 
 struct ActOut {
   float* out = nullptr;   // relu(D), pitch ldd
@@ -993,7 +1034,10 @@ static int launch_gemm(float* D, int64_t ldd, const Planes& a, const Planes& b, 
     g_attr_set[CG][A_MN][B_MN][MIX] = true;
   }
   const int64_t tiles = ceil_div(M, C::TILE_M) * ceil_div(N, UMMA_N);
-  const int max_groups = ctx().sm_count / CG;
+  // SMs left free on purpose (tnn_set_gemm_reserved_sms): room for an NCCL kernel running beside
+  // the backward pass (comm.cu)
+  const int usable_sms = std::max(CG, ctx().sm_count - g_reserved_sms);
+  const int max_groups = usable_sms / CG;
   // Tail split (see the kernel): when the tile count leaves a ragged last wave, the tiles of that
   // wave are cut along K so it runs short and full.  Measured on the 4096x4096x8192 dW product
   // (256 tiles, 74 CTA pairs): see profiles/.  Splitting EVERY tile instead lost time (1.20 ms vs
@@ -1039,7 +1083,7 @@ static int launch_gemm(float* D, int64_t ldd, const Planes& a, const Planes& b, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(1);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, ma_l16, mb_hi, mb_lo, mb_l16, D, ldd, (int)M, (int)N, (int)K, bias, flags, t_full, tail_split, g_tile_flags, g_group_m,
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, ma_l16, mb_hi, mb_lo, mb_l16, D, ldd, (int)M, (int)N, (int)K, bias, flags | g_exp_flags, t_full, tail_split, g_tile_flags, g_group_m,
                               act.out, act.hi, act.lo, (__nv_bfloat16*)act.l16, act.ld, act.mask_src));
   ctx().launches++;
   prof_end(1);
@@ -1075,6 +1119,12 @@ static int gemm_common(const char* who, bool mix, float* D, int64_t ldd, const t
   if (!env_read) {
     const char* e = getenv("TNN_GEMM_CG");
     if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
+    const char* rs = getenv("TNN_GEMM_RESERVED_SMS");
+    if (rs && !tc::g_reserved_sms) tc::g_reserved_sms = atoi(rs);
+    const char* ex = getenv("TNN_EXP_SKIP_H16");
+    if (ex && atoi(ex)) tc::g_exp_flags |= 64;
+    const char* ex2 = getenv("TNN_EXP_FLAGS");     // 128 = no operand fetch, 256 = no MMA (timing only)
+    if (ex2) tc::g_exp_flags |= atoi(ex2) & (64 | 128 | 256 | 512);
     const char* ks = getenv("TNN_GEMM_KSPLIT");
     if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
     env_read = true;
@@ -1128,6 +1178,12 @@ int tnn_set_gemm_group_m(int gm) {
 int tnn_set_gemm_ksplit(int ks) {
   if (ks != 0 && ks != 1 && ks != 2 && ks != 4) TNN_FAIL("tnn_set_gemm_ksplit: 0 (auto), 1 (off), 2 or 4");
   tc::g_force_ksplit = ks;
+  return 0;
+}
+
+int tnn_set_gemm_reserved_sms(int n) {
+  if (n < 0 || n > 64) TNN_FAIL("tnn_set_gemm_reserved_sms: 0..64");
+  tc::g_reserved_sms = n;
   return 0;
 }
 
