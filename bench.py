@@ -446,6 +446,7 @@ def run_b200_arm(args, cfg):
         # (bound to a name like in the timed loop: step i's graph then lives until step i+1 has
         # produced its loss, so the pool reaches its steady-state footprint during warm-up)
         loss = stepper(Tensor(x_dev[i % 2]), Tensor(y_dev[i % 2]))
+    loss = None                           # (or the timed loop would keep a third graph alive)
     be.sync()
     s_first = sampler.mark()
     ms, launches, gemm_ms, gemm_n, last_loss = timed_steps(stepper, x_dev, y_dev, args.steps, 0,

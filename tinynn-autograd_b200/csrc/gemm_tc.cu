@@ -53,7 +53,7 @@ constexpr int UMMA_K = 8;                 // tf32
 constexpr int PLANE_ROW_BYTES = BK * 4;   // 128
 constexpr int NUM_THREADS = 384;         // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1-2: epilogue
 #ifndef TNN_CHUNK_KB
-#define TNN_CHUNK_KB 4
+#define TNN_CHUNK_KB 8
 #endif
 constexpr int CHUNK_KB = TNN_CHUNK_KB;    // K blocks accumulated inside the tensor core per chunk
 constexpr uint32_t TMEM_COLS = 512;
@@ -63,19 +63,10 @@ struct Cfg {
   static constexpr int ROWS_B = UMMA_N / CG;                      // B rows staged per CTA
   static constexpr int A_BYTES = ROWS_A * PLANE_ROW_BYTES;        // one plane
   static constexpr int B_BYTES = ROWS_B * PLANE_ROW_BYTES;
-#ifdef TNN_EXP48
-  // TIMING EXPERIMENT (separate library, never shipped as the product): stages hold hi + l16 only
-  // (the bf16(x) planes alias l16: wrong numerics), 48 KB instead of 64 KB, one stage more
-  static constexpr int STAGES = CG == 1 ? 3 : 4;
-  static constexpr int STAGE_BYTES = (3 * A_BYTES + 3 * B_BYTES) / 2;
-  static constexpr int A_PLANES_BYTES = A_BYTES + A_BYTES / 2;
-  static constexpr int L16_OFF_A = 0, L16_OFF_B = 0;
-#else
   static constexpr int STAGES = CG == 1 ? 2 : 3;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi+lo of both operands
   static constexpr int A_PLANES_BYTES = 2 * A_BYTES;
   static constexpr int L16_OFF_A = A_BYTES / 2, L16_OFF_B = B_BYTES / 2;
-#endif
   static constexpr int TILE_M = ROWS_A * CG;
   static constexpr int EPI_PATCH_BYTES = 8 * 4096;                // one 32x32 fp32 patch per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_PATCH_BYTES;
@@ -432,26 +423,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t sb_hi = sa_hi + C::A_PLANES_BYTES;
           const uint32_t sb_lo = sb_hi + C::B_BYTES;
           // (flags & 64: timing experiment only -- the bf16(x) planes are not fetched, results are wrong)
-#ifdef TNN_EXP48
-          const bool exp_skip_h16 = true;
-          if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)C::STAGE_BYTES * CG);
-#else
+          // flags & 64 / 128 / 256 / 512 are TIMING EXPERIMENTS (TNN_EXP_FLAGS, results are wrong): the
+          // bf16(x) planes are not fetched / nothing is fetched / no MMA is issued / no chunk is drained
           const bool exp_skip_h16 = MIX && (flags & 64);
-          if (leader)
-            mbar_expect_tx(full_bar(stage), (uint32_t)(C::STAGE_BYTES - (exp_skip_h16 ? (C::A_BYTES + C::B_BYTES) / 2 : 0)) * CG);
-#endif
+          const uint32_t tx_bytes = (uint32_t)(C::STAGE_BYTES - (exp_skip_h16 ? (C::A_BYTES + C::B_BYTES) / 2 : 0)) * CG;
+          if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
           const int k0 = kb * BK;
           if (flags & 128) {
             // timing experiment: no operand fetch at all (the MMAs run on whatever the stage holds);
             // the transaction count armed above is satisfied by hand
-            if (leader) {
-#ifdef TNN_EXP48
-              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)), "r"((uint32_t)C::STAGE_BYTES * CG) : "memory");
-#else
-              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)),
-                           "r"((uint32_t)(C::STAGE_BYTES - (exp_skip_h16 ? (C::A_BYTES + C::B_BYTES) / 2 : 0)) * CG) : "memory");
-#endif
-            }
+            if (leader)
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)), "r"(tx_bytes) : "memory");
           } else
           if constexpr (!MIX) {
             if constexpr (A_MN) {
@@ -1121,9 +1103,7 @@ static int gemm_common(const char* who, bool mix, float* D, int64_t ldd, const t
     if (e && !tc::g_force_cg) tc::g_force_cg = atoi(e);
     const char* rs = getenv("TNN_GEMM_RESERVED_SMS");
     if (rs && !tc::g_reserved_sms) tc::g_reserved_sms = atoi(rs);
-    const char* ex = getenv("TNN_EXP_SKIP_H16");
-    if (ex && atoi(ex)) tc::g_exp_flags |= 64;
-    const char* ex2 = getenv("TNN_EXP_FLAGS");     // 128 = no operand fetch, 256 = no MMA (timing only)
+    const char* ex2 = getenv("TNN_EXP_FLAGS");     // timing experiments only, see the kernel
     if (ex2) tc::g_exp_flags |= atoi(ex2) & (64 | 128 | 256 | 512);
     const char* ks = getenv("TNN_GEMM_KSPLIT");
     if (ks && !tc::g_force_ksplit) tc::g_force_ksplit = atoi(ks);
