@@ -198,7 +198,7 @@ def test_tf32x3_better_than_plain_tf32(be):
         be.TC_MIN_MNK = old
     ref = a.astype(np.float64) @ b.astype(np.float64)
     # all-positive data is the worst case for the tensor core's round-toward-zero accumulation
-    # inside a chunk (8 K-blocks = 256 k since r02: measured 2.4e-6 here, 1.3e-6 on signed data)
+    # inside a chunk (8 K-blocks = 256 k since r02: between 2e-6 and 3e-6 here, 1.3e-6 on signed data)
     assert op_cases.rel_err(out, ref) <= 3e-6
     # and it is at least as good as numpy's own float32 product on the same data
     assert op_cases.rel_err(out, ref) <= 4 * op_cases.rel_err(a @ b, ref) + 1e-7
