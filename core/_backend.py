@@ -116,6 +116,9 @@ _SIGNATURES = {
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
     "tnn_set_gemm_reserved_sms": [_c_int],
     "tnn_one_hot": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
+    "tnn_mlp_tail_workspace": [_c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
+    "tnn_mlp_tail_step": [_c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_int,
+                          _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "tnn_nccl_unique_id": [_c_vp],
@@ -982,6 +985,58 @@ def ce_bwd(z, y, stats, q, m_global, g):
                        q.ptr, float(m_global), g.ptr):
         _raise("tnn_ce_bwd")
     return dz
+
+
+class MLPTail(object):
+    """Workspace and argument block of the fused small-MLP tail pass (tnn_mlp_tail_step) for one
+    network / batch size: layers 2..L of a Dense/ReLU MLP whose tail weights fit in shared memory."""
+
+    MAX_WIDTH = 256
+    MAX_LAYERS = 6
+    SMEM_LIMIT = 220 * 1024
+
+    def __init__(self, dims, batch, n_grad):
+        """dims = [in0, out0 = in1, ..., out_{L-1}] of the tail layers; n_grad = length of the
+        tail's stretch of the flat gradient arena (slot padding included)"""
+        L = len(dims) - 1
+        self.L, self.batch, self.n_grad = L, batch, n_grad
+        self.in_dims = (_c_i64 * L)(*dims[:-1])
+        self.out_dims = (_c_i64 * L)(*dims[1:])
+        smem, n_ctas, scratch = _c_i64(), _c_i64(), _c_i64()
+        if _lib.tnn_mlp_tail_workspace(L, self.in_dims, self.out_dims, batch, ctypes.byref(smem),
+                                       ctypes.byref(n_ctas), ctypes.byref(scratch)):
+            _raise("tnn_mlp_tail_workspace")
+        self.smem_bytes, self.n_ctas = smem.value, n_ctas.value
+        self.scratch = empty((scratch.value,), F32)   # layer inputs and dL/dz rows between the two phases
+        self.stats = zeros((2 * self.n_ctas,), F32)
+        self.loss_part = zeros((self.n_ctas,), F32)
+        self.counters = zeros((16,), F32)             # uint32 rendezvous counters, rearmed by the kernel
+
+    @classmethod
+    def eligible(cls, dims, batch):
+        init()
+        L = len(dims) - 1
+        if not (1 <= L <= cls.MAX_LAYERS) or any(d < 1 or d > cls.MAX_WIDTH for d in dims):
+            return False
+        if batch < 1 or batch > 256:
+            return False
+        floats = sum(dims[i] * (dims[i + 1] | 1) + (dims[i + 1] + 3) // 4 * 4 for i in range(L))
+        floats = (floats + 3) // 4 * 4 + 12 * sum(dims) + 4 * 256
+        return floats * 4 <= cls.SMEM_LIMIT
+
+    def run(self, ws, bs, grad_base, grad_offsets, n_grad, z1, y, m_global, dz1, loss_out):
+        """ws/bs: device arrays of the tail parameters; grad_base: DArray view at the first tail
+        parameter's gradient slot; grad_offsets: [dW_0, db_0, dW_1, ...] element offsets from it"""
+        if n_grad != self.n_grad:
+            raise ValueError("MLPTail was laid out for %d gradient elements, got %d" % (self.n_grad, n_grad))
+        wp = (_c_vp * self.L)(*[w.ptr for w in ws])
+        bp = (_c_vp * self.L)(*[b.ptr for b in bs])
+        go = (_c_i64 * (2 * self.L))(*grad_offsets)
+        if _lib.tnn_mlp_tail_step(self.L, self.in_dims, self.out_dims, wp, bp, go, grad_base.ptr, n_grad,
+                                  z1.ptr, y.ptr, _DT_CODE[y.dtype], self.batch, float(m_global), dz1.ptr,
+                                  loss_out.ptr, self.scratch.ptr, self.stats.ptr, self.loss_part.ptr,
+                                  self.counters.ptr):
+            _raise("tnn_mlp_tail_step")
 
 
 def opt_step(opt, param, step_out, grad, s0, s1, hyper):

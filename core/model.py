@@ -20,6 +20,10 @@ _ALIGN = 64  # elements; keeps every parameter slot 256-byte aligned for 128-bit
 
 class Model(object):
 
+    # train_step on a small Dense/ReLU MLP with SoftmaxCrossEntropyLoss (the examples/mnist network)
+    # records the fused small-MLP pass (csrc/mlp_fused.cu) instead of the layer-by-layer step
+    fuse_small_mlp = True
+
     def __init__(self, net, loss, optimizer):
         self.net = net
         self.loss = loss
@@ -257,8 +261,10 @@ class Model(object):
             return None
         if not self.optimizer.uses_builtin_rule():
             return None
+        plan = self._fused_mlp_plan(x, y) if self.fuse_small_mlp else None
+        body = None if plan is None else (lambda xt, yt: self._fused_mlp_step(xt, yt, plan))
         try:
-            step = _CapturedStep(self, x, y)
+            step = _CapturedStep(self, x, y, body, keepalive=plan)
         except be.BackendError:
             # something in the step cannot be recorded (a host read of a device value, an upload,
             # scratch growth): the aborted recording ran nothing, so drop what it cached and let the
@@ -272,6 +278,69 @@ class Model(object):
             step.destroy()
             return None
         return step
+
+    # ------------------------------------------------------------------ fused small-MLP step
+    def _fused_mlp_plan(self, x, y):
+        """Is this (network, loss, batch) the pattern csrc/mlp_fused.cu handles?  A Dense/ReLU stack
+        of float32 layers (run.py:59-69) whose layers after the first fit one SM's shared memory,
+        the reference's SoftmaxCrossEntropyLoss, one process.  Returns the plan or None."""
+        from core.layers import Dense, ReLU
+        from core.losses import SoftmaxCrossEntropyLoss
+        layers = self.net.layers
+        if dist.world_size() != 1 or type(self.loss) is not SoftmaxCrossEntropyLoss:
+            return None
+        if getattr(self.loss, "_weight", None) is not None:
+            return None
+        if len(layers) < 3 or len(layers) % 2 == 0:
+            return None
+        dense = layers[0::2]
+        if not all(type(l) is Dense and l.is_init for l in dense) or not all(type(l) is ReLU for l in layers[1::2]):
+            return None
+        plist = self._param_list()
+        a = self._arena
+        if a is None or not self._arena_valid(plist) or len(plist) != 2 * len(dense) or a["p"].dtype != be.F32:
+            return None
+        if x.dtype != be.F32 or x.ndim != 2 or y.ndim != 2 or y.dtype not in (be.F32, be.F64):
+            return None
+        dims = [dense[0].params["w"].shape[1]] + [l.params["w"].shape[1] for l in dense[1:]]
+        B = x.shape[0]
+        if x.shape[1] != dense[0].params["w"].shape[0] or y.shape != (B, dims[-1]):
+            return None
+        for l, d_in, d_out in zip(dense[1:], dims[:-1], dims[1:]):
+            if tuple(l.params["w"].shape) != (d_in, d_out) or tuple(l.params["b"].shape) != (1, d_out):
+                return None
+        if tuple(dense[0].params["b"].shape) != (1, dims[0]) or not be.MLPTail.eligible(dims, B):
+            return None
+        n_grad = a["g"].size - a["slots"][2][0]
+        return dict(dense=dense, dims=dims, tail=be.MLPTail(dims, B, n_grad))
+
+    def _fused_mlp_step(self, x, y, plan):
+        """zero_grad + forward + loss + backward + step of run.py:79-83 as: first-layer product,
+        the fused tail pass, first-layer gradient products, optimiser.  Returns the loss Tensor."""
+        from core.tensor import Tensor
+        a, dense, dims = self._arena, plan["dense"], plan["dims"]
+        be.new_split_epoch()
+        w1, b1 = dense[0].params["w"], dense[0].params["b"]
+        xd = x._data
+        B = xd.shape[0]
+        z1 = be.matmul(xd, w1._data, bias=b1._data)
+        off_tail = a["slots"][2][0]
+        n_grad = a["g"].size - off_tail
+        offsets = [o - off_tail for (o, _) in a["slots"][2:]]
+        dz1 = be.empty((B, dims[0]), be.F32)
+        loss = be.empty((), be.F32)
+        plan["tail"].run([l.params["w"]._data for l in dense[1:]], [l.params["b"]._data for l in dense[1:]],
+                         a["g"].view((n_grad,), off_tail), offsets, n_grad, z1, y._data, B, dz1, loss)
+        if be.dense_bwd_grouped_ok(B, w1.shape[0], w1.shape[1], be.F32):
+            be.dense_bwd_grouped(dz1, xd, w1._data, None, False, w1._gslot, False, b1._gslot, False)
+        else:
+            be.matmul(xd, dz1, ta=True, out=w1._gslot)
+            be.colsum(dz1, out=b1._gslot)
+        self.optimizer.apply_fused(a["p"], a["g"])
+        for p in a["params"]:
+            p._touch()
+            p._drop_grad()
+        return Tensor(loss)
 
     def zero_grad(self):
         be.new_split_epoch()
@@ -302,9 +371,13 @@ def _pickled_values(t):
 class _CapturedStep(object):
     """The training step of one batch shape, recorded once and replayed (Model.train_step)."""
 
-    def __init__(self, model, x, y):
+    def __init__(self, model, x, y, body=None, keepalive=None):
+        """body(x_tensor, y_tensor) -> loss Tensor is what gets recorded (default: the five lines);
+        keepalive: whatever owns device buffers the recording names besides its own temporaries"""
         from core.tensor import Tensor
         self.model = model
+        self.keepalive = keepalive
+        body = body or model._eager_step
         self.x = be.empty(x.shape, x.dtype)          # the graph reads its batch from here
         self.y = be.empty(y.shape, y.dtype)
         self.hyper = be.zeros((8,), be.F64)
@@ -316,7 +389,7 @@ class _CapturedStep(object):
         opt._hyper_dev = self.hyper
         try:
             with self.graph.capture():
-                loss = model._eager_step(Tensor(self.x), Tensor(self.y))
+                loss = body(Tensor(self.x), Tensor(self.y))
                 self.loss = loss._data                # stays allocated: the graph writes it
         finally:
             opt._hyper_dev = None

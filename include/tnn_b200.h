@@ -272,6 +272,29 @@ int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                const void* stats_dev, const void* q_dev, double m_global, const void* g_dev);
 
+/* Small-MLP tail in ONE launch (examples/mnist/run.py:59-84 at batch 128: layers 2..L of the
+ * 784-200-100-70-30-10 network).  Phase 1, 4 batch rows per CTA with the tail's weights resident in
+ * shared memory: forward of the tail Dense/ReLU layers (layers.py:43-49, 97-98), the global-softmax
+ * cross-entropy (losses.py:24-32; one grid-wide exchange of (max, sum-exp) pairs), dL/dz and the dX
+ * chain with ReLU masks (ops.py:156-157, 336-343).  Phase 2, after a grid-wide rendezvous: the tail's
+ * dW / db (ops.py:159-160, 49-55) as 32x32 tiles over all batch rows, each element summed by one
+ * thread in row order (deterministic), written straight into `grad`.
+ *   in_dims/out_dims[n_layers]  widths of the tail layers (each <= 256, chained); batch <= 256
+ *   w[l] [in,out], b[l] [out]   float32 parameters
+ *   grad_off[2*l], [2*l+1]      element offsets of dW_l, db_l relative to `grad` (the first tail
+ *                               parameter's slot of the flat gradient arena; n_grad bounds them)
+ *   z1 [B,in[0]]                pre-activation of the layer BELOW the tail (its ReLU is applied here)
+ *   y [B,out[L-1]]              labels, y_dtype TNN_F32 or TNN_F64;  m_global = batch size in the loss
+ *   dz1 [B,in[0]]               receives dL/dz1 (masked): input of the first layer's own backward launch
+ *   workspace                   scratch [scratch_floats], stats [2*n_ctas], loss_part [n_ctas],
+ *                               counters [16 x uint32, zeroed once]; sizes from tnn_mlp_tail_workspace */
+int tnn_mlp_tail_workspace(int n_layers, const int64_t* in_dims, const int64_t* out_dims, int64_t batch,
+                           int64_t* smem_bytes, int64_t* n_ctas, int64_t* scratch_floats);
+int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_dims, const void* const* w,
+                      const void* const* b, const int64_t* grad_off, void* grad, int64_t n_grad,
+                      const void* z1, const void* y, int y_dtype, int64_t B, double m_global, void* dz1,
+                      void* loss_out, void* scratch, void* stats, void* loss_part, void* counters);
+
 /* fused optimizer step on flat buffers (optimizer.py:12-35 flatten + _compute_step + model.py:59-61
  * param += step).  s0/s1 are the optimizer state vectors (Adam m,v; RMSProp ms,mom; ...), h[] the
  * hyper-parameters:

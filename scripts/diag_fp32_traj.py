@@ -14,7 +14,7 @@ import ref_fp32  # noqa: E402
 import ref_numpy as R  # noqa: E402
 
 
-def run(kind):
+def run(kind, fused=False):
     from core.layers import Dense, ReLU
     from core.losses import SoftmaxCrossEntropyLoss
     from core.model import Model
@@ -47,26 +47,31 @@ def run(kind):
     for k, batch in enumerate(BatchIterator(batch_size=128)(Tensor(x), Tensor(onehot))):
         if k == 100:
             break
-        model.zero_grad()
-        loss = loss_layer.loss(model.forward(batch.inputs), batch.targets)
-        loss.backward()
-        grads = [p.grad.copy() for layer in net.get_parameters() for p in layer.values()]
-        model.step()
+        if fused:
+            loss = model.train_step(batch.inputs, batch.targets)
+            grads = None
+        else:
+            model.zero_grad()
+            loss = loss_layer.loss(model.forward(batch.inputs), batch.targets)
+            loss.backward()
+            grads = [p.grad.copy() for layer in net.get_parameters() for p in layer.values()]
+            model.step()
         rl, rg = ref.loss_and_grads(xs[k * 128:(k + 1) * 128], ys[k * 128:(k + 1) * 128])
         ref.opt.step(ref.params(), rg)
         params = [p.values for layer in net.get_parameters() for p in layer.values()]
-        gerr = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)) for a, b in zip(grads, rg))
-        perr = max(float(np.max(np.abs(a - b))) for a, b in zip(params, ref.params()))
+        gerr = -1.0 if grads is None else max(
+            float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)) for a, b in zip(grads, rg))
+        perr = [float(np.max(np.abs(a - b))) for a, b in zip(params, ref.params())]
         rows.append(dict(step=k, loss=float(loss.values), d_gold=abs(float(loss.values) - gold[k]),
                          d_ref32=abs(float(loss.values) - rl), ref32_d_gold=abs(rl - gold[k]),
                          grad_rel=gerr, param_abs=perr))
     worst = max(rows, key=lambda r: r["d_gold"])
-    print(json.dumps(dict(kind=kind, max_d_gold=worst["d_gold"], at=worst["step"],
+    print(json.dumps(dict(kind=kind, fused=fused, max_d_gold=worst["d_gold"], at=worst["step"],
                           max_ref32_d_gold=max(r["ref32_d_gold"] for r in rows))))
-    for r in rows[:12] + rows[12::8]:
+    for r in rows[:28] + rows[28::8]:
         print(json.dumps(r))
 
 
 if __name__ == "__main__":
     for kind in ("mnist_traj", "mnist_learn_traj"):
-        run(kind)
+        run(kind, fused="--fused" in sys.argv)

@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtnn_b200.so")
 
 SOURCES = ["runtime.cu", "elementwise.cu", "reduce.cu", "layout.cu", "gemm_simt.cu",
-           "gemm_tc.cu", "fused.cu", "comm.cu"]
+           "gemm_tc.cu", "fused.cu", "mlp_fused.cu", "comm.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "math.cuh"),
            os.path.join(ROOT, "include", "tnn_b200.h")]
 
