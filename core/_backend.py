@@ -353,6 +353,49 @@ class LazyReLU(DArray):
         return self._materialise().buf
 
 
+class LazyRows(DArray):
+    """src[idx[lo:hi], ...] that is only gathered when somebody asks for its address: a mini-batch of
+    a shuffled epoch (utils/data_iterator.py:24-33, `inputs[idx]` then `inputs[start:end]`) named by a
+    window of the epoch's permutation instead of being cut out of a shuffled copy of the data set.
+    A recorded training step gathers the rows straight into its input buffer (gather_into)."""
+    __slots__ = ("_src", "_idx", "_real")
+
+    def __init__(self, src, idx_window):
+        self._src = src
+        self._idx = idx_window           # device int64 view, one entry per row
+        self._real = None
+        self.shape = (idx_window.size,) + tuple(src.shape[1:])
+        self.dtype = src.dtype
+        self.size = _prod(self.shape)
+        self.split = None
+        self.aux = None
+
+    def gather_into(self, dst):
+        """dst (same shape) <- the rows, one kernel, no intermediate"""
+        assert dst.size == self.size and dst.dtype == self.dtype
+        n = self.shape[0]
+        row = _prod(self.shape[1:])
+        if self.size and _lib.tnn_gather_rows(_DT_CODE[self.dtype], dst.ptr, self._src.ptr, self._idx.ptr, n,
+                                              row, self._src.shape[0]):
+            _raise("tnn_gather_rows")
+
+    def _materialise(self):
+        if self._real is None:
+            self._real = gather_rows(self._src, self._idx, self.shape[0])
+        return self._real
+
+    @property
+    def ptr(self):
+        return self._materialise().ptr
+
+    @property
+    def buf(self):
+        return self._materialise().buf
+
+    def view(self, shape, offset_elems=0):
+        return self._materialise().view(shape, offset_elems)
+
+
 def device_dtype(np_dtype):
     """dtype policy: float32 stays float32; everything else (ints, bools, float64, Python
     numbers) is computed in float64 so the reference's exact-equality tests hold."""

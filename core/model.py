@@ -400,8 +400,11 @@ class _CapturedStep(object):
 
     def run(self, x, y):
         from core.tensor import Tensor
-        be.copy_into(self.x, x._data)
-        be.copy_into(self.y, y._data)
+        for dst, src in ((self.x, x._data), (self.y, y._data)):
+            if isinstance(src, be.LazyRows) and src._real is None:
+                src.gather_into(dst)        # rows perm[start:end] straight into the graph's input
+            else:
+                be.copy_into(dst, src)
         self.model.optimizer.upload_hyper(self.hyper)
         self.graph.replay()
         for p in self.plist:

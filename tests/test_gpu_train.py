@@ -338,6 +338,68 @@ def test_prefetch_iterator_delivers_the_right_rows():
     feed.close()
 
 
+def test_batch_iterator_gathers_by_permutation_window():
+    """utils/data_iterator.py:22-34 on device Tensors: each batch is rows perm[start:end] of the data
+    set, gathered on demand (no shuffled copy of the whole set is ever made), identical to the
+    reference's `inputs[idx]` then `inputs[start:end]` with the same seed, short last batch included"""
+    import core._backend as be
+    from core.tensor import Tensor
+    from utils.data_iterator import BatchIterator
+    rng = np.random.RandomState(3)
+    n, d = 50000, 784
+    x = rng.rand(n, d).astype(np.float32)
+    y = np.eye(10)[rng.randint(0, 10, n)]
+    tx, ty = Tensor(x), Tensor(y)
+    be.sync()
+    before = be.pool_stats()["reserved"]
+    np.random.seed(11)
+    sizes, checked = [], 0
+    for k, batch in enumerate(BatchIterator(batch_size=128)(tx, ty)):
+        sizes.append(len(batch.inputs))
+        if k in (0, 1, 200, 390):
+            if k == 0:
+                np.random.seed(11)
+                order = np.arange(n)
+                np.random.shuffle(order)
+            lo = k * 128
+            assert np.array_equal(batch.inputs.values, x[order[lo:lo + 128]])
+            assert np.array_equal(batch.targets.values, y[order[lo:lo + 128]])
+            checked += 1
+    assert sizes == [128] * 390 + [80] and checked == 4
+    # the epoch allocated the permutation (400 KB) and a few batches, not a second copy of x (157 MB)
+    assert be.pool_stats()["reserved"] - before < 16 * 1024 * 1024
+    # a tensor that takes part in autograd keeps the reference's differentiable getitem path
+    np.random.seed(11)
+    tg = Tensor(x[:300], requires_grad=True)
+    first = next(iter(BatchIterator(batch_size=128)(tg, Tensor(y[:300]))))
+    assert first.inputs.requires_grad and len(first.inputs.dependency) == 1
+
+
+def test_train_step_takes_gathered_batches_directly():
+    """Model.train_step on BatchIterator batches: the recorded step gathers rows perm[start:end]
+    straight into its input buffers; same losses and parameters as feeding materialised batches"""
+    from core.tensor import Tensor
+    from utils.data_iterator import BatchIterator
+    rng = np.random.RandomState(5)
+    x = rng.rand(1000, 48).astype(np.float32)
+    y = np.eye(10)[rng.randint(0, 10, 1000)]
+    results = []
+    for lazy in (True, False):
+        np.random.seed(7)
+        net, model, _ = _build([32, 16, 10])
+        np.random.seed(9)
+        losses = []
+        for batch in BatchIterator(batch_size=128)(Tensor(x), Tensor(y)):
+            xb, yb = batch.inputs, batch.targets
+            if not lazy:
+                xb, yb = Tensor(xb.values), Tensor(yb.values)
+            losses.append(float(model.train_step(xb, yb).values))
+        results.append((losses, [p.values.copy() for layer in net.get_parameters() for p in layer.values()]))
+    assert results[0][0] == results[1][0] and len(results[0][0]) == 8
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.array_equal(a, b)
+
+
 def test_predict_builds_no_graph_and_matches_forward():
     """Model.predict / ops.no_grad: same values as forward(), no autograd graph, training unaffected"""
     import core.ops as ops

@@ -2,9 +2,12 @@
 
 BatchIterator keeps the reference's interface (utils/data_iterator.py): called with (inputs,
 targets) it yields Batch(inputs, targets) namedtuples, reshuffling once per call with numpy's
-global generator.  On device Tensors the shuffle is ONE row-gather kernel and every mini-batch is a
-zero-copy row view (the two getitem patterns of SURVEY 8a/a21); on numpy arrays it is plain
-indexing.
+global generator.  On device Tensors the epoch's permutation is uploaded once (8 bytes per row) and
+every mini-batch is "rows perm[start:end] of the data set": gathered by one kernel per tensor when
+the batch is used -- or straight into a recorded step's input buffer (Model.train_step) -- so the
+shuffled copy of the whole data set the reference makes (`inputs[idx]`, 157 MB for MNIST) never
+exists.  Tensors that require grad take the reference's two differentiable getitem steps instead;
+on numpy arrays it is plain indexing.
 
 PrefetchIterator is the host-fed variant: the data set stays in (pinned) host memory and batch
 i+1 is copied to the GPU on the copy stream while batch i trains, double-buffered.
@@ -27,6 +30,12 @@ def _batch_bounds(n_rows, batch_size):
     return [(lo, min(lo + batch_size, n_rows)) for lo in range(0, n_rows, batch_size)]
 
 
+def _plain_device_tensors(*tensors):
+    """device Tensors that take no part in autograd (data, not parameters) and have rows to gather"""
+    from core.tensor import Tensor
+    return all(isinstance(t, Tensor) and not t.requires_grad and t.ndim >= 1 for t in tensors)
+
+
 class BatchIterator(BaseIterator):
 
     def __init__(self, batch_size=32, shuffle=True):
@@ -38,9 +47,22 @@ class BatchIterator(BaseIterator):
         if self.shuffle:
             order = np.arange(n_rows)
             np.random.shuffle(order)            # the reference's RNG call (data_iterator.py:25-26)
+            if _plain_device_tensors(inputs, targets):
+                yield from self._gathered_batches(inputs, targets, order)
+                return
             inputs, targets = inputs[order], targets[order]
         for lo, hi in _batch_bounds(n_rows, self.batch_size):
             yield Batch(inputs=inputs[lo:hi], targets=targets[lo:hi])
+
+    def _gathered_batches(self, inputs, targets, order):
+        """fused `x[idx][start:end]`: each batch is a LazyRows window of the uploaded permutation"""
+        import core._backend as be
+        from core.tensor import Tensor
+        idx_dev = be.upload_index(order)
+        for lo, hi in _batch_bounds(len(order), self.batch_size):
+            window = idx_dev.view((hi - lo,), lo)
+            yield Batch(inputs=Tensor(be.LazyRows(inputs._data, window)),
+                        targets=Tensor(be.LazyRows(targets._data, window)))
 
 
 class PrefetchIterator(BaseIterator):
