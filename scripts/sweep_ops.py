@@ -4,9 +4,14 @@ size against the measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs).
     python scripts/sweep_ops.py [--max-log2 30] [--cpu] > gpurun_out/sweep.json
 
 Algorithmic bytes per element (fp32): add/mul 12, bias-add 8, relu fwd 8, relu bwd 12,
-unbroadcast (R,1024)->(1,1024) 4, Adam 28.  Each timing is the best of 10 launches with CUDA
-events on the compute stream after 3 warm-ups; the L2 is flushed before every timed launch for
-sizes whose working set fits in it.  With --cpu the numpy oracle's ops are timed next to it."""
+unbroadcast (R,1024)->(1,1024) 4, Adam 28.
+
+Timing (r02): for every (op, size) K launches over K ROTATING buffer sets -- K chosen so the sets
+together exceed twice the L2, every launch therefore reads cold data from HBM -- are recorded into
+one CUDA graph and replayed; time = best of 5 replays / K, CUDA events on the compute stream.  A
+replayed graph has no host in the loop, so the small sizes measure the kernel (launch ramp
+included), not the Python call that r01's one-launch-per-event-pair timing was bound by.
+With --cpu the numpy oracle's ops are timed next to it."""
 import argparse
 import json
 import os
@@ -22,19 +27,26 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import core._backend as be  # noqa: E402
 
 
-def timed(fn, flush, reps=10, warm=3):
-    for _ in range(warm):
-        fn()
+def timed_rotating(make_launch, n_sets, reps=5):
+    """make_launch(k) issues the op on buffer set k; returns ms per launch"""
+    for k in range(n_sets):           # eager warm-up (scratch growth, lazily allocated counters)
+        make_launch(k)
+    be.sync()
+    g = be.StepGraph()
+    with g.capture():
+        for k in range(n_sets):
+            make_launch(k)
+    g.replay()
+    be.sync()
     best = 1e30
     e0, e1 = be.Event(), be.Event()
     for _ in range(reps):
-        if flush:
-            be.l2_flush()
         e0.record()
-        fn()
+        g.replay()
         e1.record()
         best = min(best, e1.elapsed_ms_since(e0))
-    return best
+    g.destroy()
+    return best / n_sets
 
 
 def main():
@@ -50,30 +62,34 @@ def main():
     for lg in range(20, args.max_log2 + 1, 2):
         n = 1 << lg
         R_, C_ = n // 1024, 1024
-        a = be.full((R_, C_), 0.5, be.F32)
-        b = be.full((R_, C_), 0.25, be.F32)
-        out = be.empty((R_, C_), be.F32)
+        # rotating sets: together more than twice the L2 (4 tensors of n floats per set), 2..48 sets
+        n_sets = int(min(48, max(2, -(-2 * l2 // (4 * n * 4)))))
+        sets = []
+        for k in range(n_sets):
+            sets.append(dict(a=be.full((R_, C_), 0.5, be.F32), b=be.full((R_, C_), 0.25, be.F32),
+                             out=be.empty((R_, C_), be.F32), cs=be.empty((1, C_), be.F32),
+                             v=be.full((R_, C_), 0.25, be.F32)))
         bias = be.full((1, C_), 0.125, be.F32)
-        cs = be.empty((1, C_), be.F32)
-        flush = 3 * n * 4 <= 2 * l2
-        m = be.zeros((n,), be.F32)
-        v = be.zeros((n,), be.F32)
         h = [1e-3, 0.9, 0.999, 1e-8, 0.1, 0.001]
         ops = [
-            ("add", 12, lambda: be.ew(be.ADD, a, b, out=out)),
-            ("mul", 12, lambda: be.ew(be.MUL, a, b, out=out)),
-            ("bias_add", 8, lambda: be.ew(be.ADD, a, bias, out=out)),
-            ("relu_fwd", 8, lambda: be._lib.tnn_relu_fwd(0, out.ptr, a.ptr, n)),
-            ("relu_bwd", 12, lambda: be._lib.tnn_relu_bwd(0, out.ptr, b.ptr, a.ptr, n)),
-            ("unbroadcast_colsum", 4, lambda: be.colsum(a, out=cs)),
-            ("adam", 28, lambda: be.opt_step(be.OPT_ADAM, a.view((n,)), None, b.view((n,)), m, v, h)),
+            ("add", 12, lambda k: be.ew(be.ADD, sets[k]["a"], sets[k]["b"], out=sets[k]["out"])),
+            ("mul", 12, lambda k: be.ew(be.MUL, sets[k]["a"], sets[k]["b"], out=sets[k]["out"])),
+            ("bias_add", 8, lambda k: be.ew(be.ADD, sets[k]["a"], bias, out=sets[k]["out"])),
+            ("relu_fwd", 8, lambda k: be._lib.tnn_relu_fwd(0, sets[k]["out"].ptr, sets[k]["a"].ptr, n)),
+            ("relu_bwd", 12, lambda k: be._lib.tnn_relu_bwd(0, sets[k]["out"].ptr, sets[k]["b"].ptr,
+                                                            sets[k]["a"].ptr, n)),
+            ("unbroadcast_colsum", 4, lambda k: be.colsum(sets[k]["a"], out=sets[k]["cs"])),
+            # Adam: param = out, grad = b, m = a, v = v (28 B/elem: g, m, v, p read; m, v, p written)
+            ("adam", 28, lambda k: be.opt_step(be.OPT_ADAM, sets[k]["out"].view((n,)), None,
+                                               sets[k]["b"].view((n,)), sets[k]["a"].view((n,)),
+                                               sets[k]["v"].view((n,)), h)),
         ]
         for name, bpe, fn in ops:
-            ms = timed(fn, flush)
+            ms = timed_rotating(fn, n_sets)
             gbs = n * bpe / (ms * 1e-3) / 1e9
             rows.append(dict(op=name, log2_n=lg, bytes_per_elem=bpe, ms=ms, gbs=gbs,
-                             frac_of_measured_hbm=gbs / hbm, l2_flushed=flush))
-        del a, b, out, m, v
+                             frac_of_measured_hbm=gbs / hbm, rotating_sets=n_sets))
+        del sets
     result = dict(hbm_peak_gbs=hbm, rows=rows)
     if args.cpu:
         import ref_numpy as R

@@ -9,6 +9,7 @@
 // a shared-memory tree, the per-chunk partials are written to scratch and a second launch of the
 // same kernel folds them in index order.  No floating-point atomics anywhere.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -100,10 +101,51 @@ reduce_row_warp_kernel(T* out, const T* x, int64_t outer, int64_t red) {
 // ---- inner > 1: a CTA owns 32 column slots (128-bit each when vectorised) x a chunk of rows ------
 // thread (tx, ty) of the 32 x 8 block walks rows lo+ty, lo+ty+8, ... of its column slot (coalesced
 // across tx), the 8 row lanes are folded through shared memory in fixed order.
+// rows lo+ty, lo+ty+8, ... < hi of one column slot, 8 independent loads in flight per thread (small
+// reductions are a handful of DRAM round trips: the fewer, the better), combined in row order
+template <int RED, typename T, int VEC>
+__device__ __forceinline__ void col_accumulate(const T* __restrict__ base, int64_t lo, int64_t hi,
+                                               int64_t inner, int ty, T (&acc)[VEC]) {
+  using V = typename std::conditional<VEC == 1, T, typename std::conditional<sizeof(T) == 4, float4, double2>::type>::type;
+  union U {
+    V v;
+    T e[VEC];
+  };
+  int64_t r = lo + ty;
+  for (; r + 56 < hi; r += 64) {
+    U u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i].v = *reinterpret_cast<const V*>(base + (r + 8 * i) * inner);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = red_op<RED, T>(acc[k], u[i].e[k]);
+  }
+  if (r < hi) {
+    // the tail as ONE more batch of predicated loads (a serial tail would be up to seven exposed DRAM
+    // round trips -- most of the time of a 64 MB reduction)
+    U u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r + 8 * i < hi) u[i].v = *reinterpret_cast<const V*>(base + (r + 8 * i) * inner);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r + 8 * i < hi) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = red_op<RED, T>(acc[k], u[i].e[k]);
+      }
+  }
+}
+
+// One launch also when the rows are split across CTAs: every CTA parks its partial in `stage`, and
+// the LAST one to arrive for a column block (a counter per block, reset by that CTA) folds the
+// nsplit partials -- always in split order, so the result does not depend on which CTA folds.
 template <int RED, typename T, int VEC>
 __global__ void __launch_bounds__(256)
-reduce_col_kernel(T* out, const T* x, int64_t red, int64_t inner, int nsplit) {
+reduce_col_kernel(T* out, T* stage, const T* x, int64_t red, int64_t inner, int nsplit,
+                  unsigned int* counters) {
   __shared__ T sm[8][32 * VEC + 1];
+  __shared__ bool is_last;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t ncol = inner / VEC;
   const int64_t col = (int64_t)blockIdx.x * 32 + tx;
@@ -116,57 +158,54 @@ reduce_col_kernel(T* out, const T* x, int64_t red, int64_t inner, int nsplit) {
   T acc[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = red_identity<RED, T>();
-  if (col < ncol) {
-    const T* base = x + (o * red) * inner + col * VEC;
-    if constexpr (VEC == 1) {
-      int64_t r = lo + ty;
-      for (; r + 24 < hi; r += 32) {
-        T v0 = base[r * inner], v1 = base[(r + 8) * inner], v2 = base[(r + 16) * inner],
-          v3 = base[(r + 24) * inner];
-        acc[0] = red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[0], v0), v1), v2), v3);
-      }
-      for (; r < hi; r += 8) acc[0] = red_op<RED, T>(acc[0], base[r * inner]);
-    } else {
-      using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-      union U {
-        V v;
-        T e[VEC];
-      };
-      int64_t r = lo + ty;
-      for (; r + 24 < hi; r += 32) {
-        U u0, u1, u2, u3;
-        u0.v = *reinterpret_cast<const V*>(base + r * inner);
-        u1.v = *reinterpret_cast<const V*>(base + (r + 8) * inner);
-        u2.v = *reinterpret_cast<const V*>(base + (r + 16) * inner);
-        u3.v = *reinterpret_cast<const V*>(base + (r + 24) * inner);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          acc[k] = red_op<RED, T>(
-              red_op<RED, T>(red_op<RED, T>(red_op<RED, T>(acc[k], u0.e[k]), u1.e[k]), u2.e[k]),
-              u3.e[k]);
-      }
-      for (; r < hi; r += 8) {
-        U u;
-        u.v = *reinterpret_cast<const V*>(base + r * inner);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = red_op<RED, T>(acc[k], u.e[k]);
-      }
-    }
-  }
+  if (col < ncol) col_accumulate<RED, T, VEC>(x + (o * red) * inner + col * VEC, lo, hi, inner, ty, acc);
 #pragma unroll
   for (int k = 0; k < VEC; ++k) sm[ty][tx * VEC + k] = acc[k];
   __syncthreads();
+  T* dst1 = nsplit > 1 ? stage + ((o * nsplit + s) * inner) : out + o * inner;
   if (ty == 0 && col < ncol) {
-    T* dst = out + ((o * nsplit + s) * inner) + col * VEC;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       T r = sm[0][tx * VEC + k];
 #pragma unroll
       for (int j = 1; j < 8; ++j) r = red_op<RED, T>(r, sm[j][tx * VEC + k]);
-      dst[k] = r;
+      dst1[col * VEC + k] = r;
+    }
+  }
+  if (nsplit == 1) return;
+  // ---- last CTA of this column block folds the partials ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* cnt = counters + o * gridDim.x + blockIdx.x;
+    const unsigned int prev = atomicAdd(cnt, 1u);
+    is_last = prev == (unsigned int)nsplit - 1;
+    if (is_last) *cnt = 0u;                      // rearmed for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = red_identity<RED, T>();
+  if (col < ncol)
+    col_accumulate<RED, T, VEC>(stage + (o * nsplit) * inner + col * VEC, 0, nsplit, inner, ty, acc);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) sm[ty][tx * VEC + k] = acc[k];
+  __syncthreads();
+  if (ty == 0 && col < ncol) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      T r = sm[0][tx * VEC + k];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) r = red_op<RED, T>(r, sm[j][tx * VEC + k]);
+      out[o * inner + col * VEC + k] = r;
     }
   }
 }
+
+static unsigned int* g_col_counters = nullptr;     // one per (outer, column block), zero between launches
+constexpr int64_t MAX_COL_COUNTERS = 1 << 16;
 
 template <int RED, typename T>
 static int reduce_impl(T* out, const T* x, int64_t outer, int64_t red, int64_t inner) {
@@ -224,36 +263,38 @@ static int reduce_impl(T* out, const T* x, int64_t outer, int64_t red, int64_t i
   // small inputs (the bias gradients of the MNIST-sized layers: 128 x 200 and below) are bound by
   // launch latency, not bandwidth: one stage, one launch
   if (gx * outer < target_ctas && outer * red * inner > (int64_t(1) << 18)) {
-    nsplit = std::min<int64_t>(ceil_div(target_ctas, gx * outer), ceil_div(red, 64));
+    // CTAs per SM for the split (each at least 64 rows).  Measured on (2^24 / 1024, 1024) -> (1, 1024),
+    // graph-replayed over rotating buffers: 1 -> 17.8 us, 2 -> 15.3, 3 -> 14.9, 4 -> 15.7, 8 -> 18.2,
+    // 16 -> 18.5 (more partials make the last-block fold longer; fewer starve the load pipeline)
+    static int col_ctas_per_sm = -1;
+    if (col_ctas_per_sm < 0) {
+      const char* e = getenv("TNN_COLSUM_CTAS_PER_SM");
+      col_ctas_per_sm = e ? atoi(e) : 3;
+      if (col_ctas_per_sm < 1) col_ctas_per_sm = 1;
+    }
+    const int64_t want = (int64_t)c.sm_count * col_ctas_per_sm;
+    nsplit = std::min<int64_t>(ceil_div(want, gx * outer), ceil_div(red, 64));
     if (nsplit < 1) nsplit = 1;
   }
   if (outer * nsplit > 65535) {
     nsplit = std::max<int64_t>(1, 65535 / outer);
     if (outer > 65535) TNN_FAIL("tnn_reduce: outer extent above 65535 with inner > 1 is not supported");
   }
-  T* stage_out = out;
   void* scratch = nullptr;
   if (nsplit > 1) {
-    if (get_scratch((size_t)(outer * nsplit * inner) * sizeof(T), &scratch)) return 1;
-    stage_out = (T*)scratch;
+    if (gx * outer > MAX_COL_COUNTERS) nsplit = 1;
+    else if (get_scratch((size_t)(outer * nsplit * inner) * sizeof(T), &scratch)) return 1;
   }
-  bool vec_out = vec && ((reinterpret_cast<uintptr_t>(stage_out) & 15) == 0);
-  (void)vec_out;
+  if (nsplit > 1 && !g_col_counters) {
+    TNN_CUDA(cudaMalloc(&g_col_counters, MAX_COL_COUNTERS * sizeof(unsigned int)));
+    TNN_CUDA(cudaMemsetAsync(g_col_counters, 0, MAX_COL_COUNTERS * sizeof(unsigned int), st));
+  }
   dim3 grid((unsigned)gx, (unsigned)(outer * nsplit));
   if (vec)
-    reduce_col_kernel<RED, T, VW><<<grid, 256, 0, st>>>(stage_out, x, red, inner, (int)nsplit);
+    reduce_col_kernel<RED, T, VW><<<grid, 256, 0, st>>>(out, (T*)scratch, x, red, inner, (int)nsplit, g_col_counters);
   else
-    reduce_col_kernel<RED, T, 1><<<grid, 256, 0, st>>>(stage_out, x, red, inner, (int)nsplit);
+    reduce_col_kernel<RED, T, 1><<<grid, 256, 0, st>>>(out, (T*)scratch, x, red, inner, (int)nsplit, g_col_counters);
   TNN_POST_LAUNCH();
-  if (nsplit > 1) {
-    // (outer, nsplit, inner) -> (outer, inner), single chunk per column
-    dim3 grid2((unsigned)gx, (unsigned)outer);
-    if (vec)
-      reduce_col_kernel<RED, T, VW><<<grid2, 256, 0, st>>>(out, (const T*)scratch, nsplit, inner, 1);
-    else
-      reduce_col_kernel<RED, T, 1><<<grid2, 256, 0, st>>>(out, (const T*)scratch, nsplit, inner, 1);
-    TNN_POST_LAUNCH();
-  }
   return 0;
 }
 
