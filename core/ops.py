@@ -17,11 +17,13 @@ import os
 import core._backend as be
 
 # ReLU-backward mask fused into the dX GEMM epilogue.  Correct and bit-identical (tested).  On the
-# tensor-core path it is 6 fewer launches per wide-MLP step, but the step is power-bound and the
-# A/B measurements showed no gain (12.79 vs 12.84 ms/step; 11.58 vs 11.58 with the mixed split), so
-# there it is opt-in.  On the SIMT path (MNIST-sized layers, launch-bound) it is always on: one
-# launch less per hidden layer.
-FUSE_RELU_BWD = os.environ.get("TNN_FUSE_RELU_BWD", "0") != "0"
+# tensor-core path it is 6 fewer launches per wide-MLP step (3 relu_bwd + 3 operand splits: the
+# masked gradient leaves the epilogue with its planes).  r01 measured no gain (11.58 vs 11.58 ms);
+# with r02's longer accumulator chunks the epilogue has more slack and the A/B is 11.07 / 11.08 ms
+# fused against 11.19 ms unfused (same box, alternating runs), so it is on by default
+# (TNN_FUSE_RELU_BWD=0 turns it off).  On the SIMT path (MNIST-sized layers, launch-bound) it is
+# always on: one launch less per hidden layer.
+FUSE_RELU_BWD = os.environ.get("TNN_FUSE_RELU_BWD", "1") != "0"
 # dX, dW and db of a small Dense layer as one grouped launch (tnn_dense_bwd_simt)
 GROUP_SMALL_DENSE_BWD = os.environ.get("TNN_GROUP_DENSE_BWD", "1") != "0"
 WRITTEN_IN_PLACE = object()   # returned by a node's _fused_bwd for gradients it wrote into their slot
