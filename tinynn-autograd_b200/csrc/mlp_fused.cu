@@ -48,6 +48,10 @@ struct TailArgs {
   int64_t dz_g[MAX_LAYERS];       //                                  dL/dz of layer l's output, [B, out_l]
   int tile_first[MAX_LAYERS + 1]; // phase 2: first 32x32 dW tile of layer l (prefix sums)
   int row_ctas;                   // CTAs that own batch rows (the rest of the grid joins for phase 2)
+  // thread split of the two small products of layer l, worked out on the host (integer divisions are
+  // 100+ dependent cycles each on the device, and this kernel is a chain of short serial phases):
+  // warps per K group, K groups, k per group -- [0] forward (N = out), [1] backward (N = in)
+  int wpg[MAX_LAYERS][2], ks[MAX_LAYERS][2], per[MAX_LAYERS][2];
 };
 
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
@@ -66,19 +70,18 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 }
 
 // out[j] (j < N) = init[j] + sum_k in[k] * W(k, j) for the CTA's 4 rows at once.
-// The threads are split into KS groups along K (KS * roundup32(N) <= THREADS, KS <= 16, at least 8 k
-// per group); group partials are folded in group order.  TRANSPOSED = false: W(k, j) = ws[k * pitch + j] (forward);
+// The threads are split into KS groups along K (KS * roundup32(N) <= THREADS, at least 8 k per group;
+// the split comes from the host); group partials are folded in group order.  TRANSPOSED = false: W(k, j) = ws[k * pitch + j] (forward);
 // true: W(k, j) = ws[j * pitch + k] (backward, dA = dZ @ W^T: k runs over the layer's outputs).
 template <bool TRANSPOSED>
 __device__ __forceinline__ void small_gemm(const float4* __restrict__ in, int K, int N,
                                            const float* __restrict__ ws, int pitch,
-                                           float4* __restrict__ scratch, float4& result, bool& owner) {
-  const int npad = (N + 31) & ~31;
-  int ks = THREADS / npad;
-  if (ks > 16) ks = 16;
-  while (ks > 1 && K / ks < 8) --ks;
-  const int grp = threadIdx.x / npad, j = threadIdx.x - grp * npad;
-  const int per = (K + ks - 1) / ks;
+                                           float4* __restrict__ scratch, int wpg, int ks, int per,
+                                           float4& result, bool& owner) {
+  const int npad = wpg * 32;
+  int grp = 0, w = threadIdx.x >> 5;
+  while (w >= wpg) { w -= wpg; ++grp; }          // (warp id) / (warps per group) without a division
+  const int j = w * 32 + (threadIdx.x & 31);
   float4 acc = f4(0.f);
   if (grp < ks && j < N) {
     const int k0 = grp * per, k1 = min(K, k0 + per);
@@ -177,8 +180,10 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
       float* ws = sm + a.w_s[l];
       const int total = K * N;
       if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(wg) & 15) == 0) {
-        // all of a thread's 128-bit loads are issued before the first store (one L2 round trip,
-        // not one per element group)
+        // all of a thread's 128-bit loads are issued before the first store (one L2 round trip per
+        // batch, not one per element group); (row, column) of the first element by one division per
+        // vector, then incrementally.  (A warp-per-row variant with 4-byte loads and no division at
+        // all measured slower: 29k against 16k cycles for the 119 KB of the MNIST tail.)
         constexpr int SB = 8;
         const int nq = total / 4;
         for (int q0 = tid; q0 < nq; q0 += THREADS * SB) {
@@ -233,7 +238,7 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
       float4 acc;
       bool owner;
       small_gemm<false>(reinterpret_cast<const float4*>(sm + a.a_s[l]), K, N, sm + a.w_s[l], N | 1, scratch,
-                        acc, owner);
+                        a.wpg[l][0], a.ks[l][0], a.per[l][0], acc, owner);
       if (owner) {
         const float bj = sm[a.b_s[l] + tid];
         const float4 z = make_float4(acc.x + bj, acc.y + bj, acc.z + bj, acc.w + bj);
@@ -337,7 +342,7 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
       }
       float4 acc;
       bool owner;
-      small_gemm<true>(gz, N, K, sm + a.w_s[l], N | 1, scratch, acc, owner);
+      small_gemm<true>(gz, N, K, sm + a.w_s[l], N | 1, scratch, a.wpg[l][1], a.ks[l][1], a.per[l][1], acc, owner);
       if (owner) {
         const float4 z = reinterpret_cast<const float4*>(sm + a.z_s[l])[tid];
         const float4 m = make_float4(z.x >= 0.f ? acc.x : acc.x * 0.f, z.y >= 0.f ? acc.y : acc.y * 0.f,
@@ -382,8 +387,9 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
     while (t >= a.tile_first[l + 1]) ++l;
     const int K = a.in[l], N = a.out[l];
     const int tiles_n = (N + 31) >> 5;
-    const int lt = t - a.tile_first[l];
-    const int i0 = (lt / tiles_n) * 32, j0 = (lt % tiles_n) * 32;
+    int lt = t - a.tile_first[l], ib = 0;
+    while (lt >= tiles_n) { lt -= tiles_n; ++ib; }
+    const int i0 = ib * 32, j0 = lt * 32;
     const float* __restrict__ ag = gscratch + a.act_g[l];
     const float* __restrict__ dg = gscratch + a.dz_g[l];
     __syncthreads();                               // previous tile's readers are done
@@ -518,6 +524,16 @@ int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_d
     a.dz_g[l] = goff;
     goff += B * out_dims[l];
     a.tile_first[l + 1] = a.tile_first[l] + ((a.in[l] + 31) / 32) * ((a.out[l] + 31) / 32);
+    for (int d = 0; d < 2; ++d) {
+      const int K = d == 0 ? a.in[l] : a.out[l], N = d == 0 ? a.out[l] : a.in[l];
+      const int npad = (N + 31) & ~31;
+      int ks = mlp::THREADS / npad;
+      if (ks > 8) ks = 8;
+      while (ks > 1 && K / ks < 8) --ks;
+      a.wpg[l][d] = npad / 32;
+      a.ks[l][d] = ks;
+      a.per[l][d] = (K + ks - 1) / ks;
+    }
   }
   off = (off + 3) & ~3;
   for (int l = 0; l <= n_layers; ++l) {
