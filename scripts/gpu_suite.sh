@@ -17,8 +17,8 @@ for s in $STAGES; do
     bench2) TNN_GEMM_CG=2 timeout 900 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cg2.log 2>&1 ;;
     mnist) timeout 600 python bench.py --workload mnist --steps 2000 --warmup 50 > gpurun_out/bench_mnist.log 2>&1; timeout 600 python bench.py --workload mnist --steps 2000 --warmup 50 --graph off --no-cpu-baseline > gpurun_out/bench_mnist_eager.log 2>&1 ;;
     sweep) timeout 900 python scripts/sweep_ops.py --cpu > gpurun_out/sweep.json 2> gpurun_out/sweep.err ;;
-    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 22 -c 3 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1; ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2>/dev/null; [ $(stat -c %s gpurun_out/prof_gemm.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/prof_gemm.ncu-rep ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_list.log 2>&1 ;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 22 -c 3 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_gemm.log 2>&1; ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2>/dev/null; [ $(stat -c %s gpurun_out/prof_gemm.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/prof_gemm.ncu-rep ;;
     dist)  timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_dist.log 2>&1 ;;
     bench_n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.log 2>&1 ;;
     bench_n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/bench_n4.log 2>&1 ;;
@@ -33,7 +33,7 @@ for s in $STAGES; do
     gemmbench2) timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1 --sustain 500 > gpurun_out/gemm_bench_mix.jsonl 2>&1; TNN_GEMM_SPLIT=tf32x3 timeout 600 python scripts/gemm_bench.py --cg 2 --ksplit 0 --group-m 1 --sustain 500 > gpurun_out/gemm_bench_tf32x3.jsonl 2>&1 ;;
     graph) timeout 900 python -m pytest tests/test_gpu_graph.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_graph.log 2>&1 ;;
     mnist_ab) for g in on off on off; do timeout 300 python bench.py --workload mnist --steps 2000 --warmup 50 --graph $g --no-cpu-baseline >> gpurun_out/bench_mnist_graph_$g.log 2>&1; done ;;
-    ncu_mnist_graph) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -s 400 -c 200 --csv --log-file gpurun_out/launches_mnist_graph.csv python bench.py --workload mnist --steps 20 --warmup 10 --graph on --no-cpu-baseline > gpurun_out/ncu_mnist_graph.log 2>&1 ;;
+    ncu_mnist_graph) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -s 100 -c 40 --csv --log-file gpurun_out/launches_mnist_graph.csv python bench.py --workload mnist --steps 20 --warmup 10 --graph on --no-cpu-baseline > gpurun_out/ncu_mnist_graph.log 2>&1 ;;
     diag)  timeout 600 python scripts/diag_fp32_traj.py > gpurun_out/diag_fp32.jsonl 2>&1 ;;
     all)   timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1 ;;
   esac
