@@ -491,11 +491,12 @@ def run_b200_arm(args, cfg):
         loss = stepper(batch.inputs, batch.targets)      # queued; the GPU starts on it
         batch = next(feed)                               # H2D of a following batch is queued in here,
                                                          # while the GPU runs the step just queued
+        read = loss.values_async()                       # D2H of this step's loss, on its own stream
         if pending is not None:
-            float(pending.values)                        # D2H read of the PREVIOUS step's loss: every
-        pending = loss                                   # step's loss reaches the host, one step late,
-                                                         # so the host never drains the GPU's queue
-    float(pending.values)                                # (inside the timed region)
+            float(pending.result())                      # the PREVIOUS step's loss is on the host now:
+        pending = read                                   # every step's loss is read, one step late, and
+                                                         # the host never drains the GPU's queue
+    float(pending.result())                              # (inside the timed region)
     e1.record()
     dist.barrier()
     e2e_ms = e1.elapsed_ms_since(e0)

@@ -115,6 +115,8 @@ _SIGNATURES = {
     "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
     "tnn_set_gemm_reserved_sms": [_c_int],
+    "tnn_d2h_async": [_c_vp, _c_vp, _c_sz, _c_vp],
+    "tnn_event_sync": [_c_vp],
     "tnn_one_hot": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
     "tnn_mlp_tail_workspace": [_c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
     "tnn_mlp_tail_step": [_c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_int,
@@ -1172,6 +1174,36 @@ def copy_stream_sync():
 def wait_prefetch():
     if _lib.tnn_compute_wait_copy():
         _raise("tnn_compute_wait_copy")
+
+
+_pinned_free = {}    # nbytes -> [PinnedArray]: read-back staging buffers are recycled
+
+
+class AsyncRead(object):
+    """Read-back of a device array that does not drain the compute stream: the copy runs on its own
+    stream after the work queued so far; result() waits for it only (later steps stay queued)."""
+
+    def __init__(self, d):
+        init()
+        self.shape, self.dtype = d.shape, d.dtype
+        nbytes = max(d.nbytes, 1)
+        free = _pinned_free.get(nbytes)
+        self.pin = free.pop() if free else PinnedArray((nbytes,), np.uint8)
+        self.event = Event()
+        self._src = d                      # keeps the block alive until the copy has run
+        self._value = None
+        if _lib.tnn_d2h_async(self.pin.ptr, d.ptr, d.nbytes, self.event.ptr):
+            _raise("tnn_d2h_async")
+
+    def result(self):
+        if self._value is None:
+            if _lib.tnn_event_sync(self.event.ptr):
+                _raise("tnn_event_sync")
+            n = int(np.prod(self.shape)) if self.shape else 1
+            self._value = np.frombuffer(self.pin.array, dtype=self.dtype, count=n).reshape(self.shape).copy()
+            _pinned_free.setdefault(self.pin.nbytes, []).append(self.pin)
+            self.pin = self._src = None
+        return self._value
 
 
 class Event(object):

@@ -82,6 +82,13 @@ class Tensor(object):
         self._host = None
         self._drop_grad()
 
+    def values_async(self):
+        """Start copying the values to the host without waiting for device work queued later; the
+        returned object's .result() gives the numpy array.  (Not in the reference's interface: there
+        `loss.values` is already host memory.  Here it lets a loop log step i's loss while step i+1
+        is running instead of draining the GPU once per step.)"""
+        return be.AsyncRead(self._data)
+
     def _drop_grad(self):
         self._grad = None
         self._grad_zero = False

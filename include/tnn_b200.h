@@ -96,6 +96,12 @@ int tnn_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* n_cuda_
 int tnn_pool_trim(void);
 int tnn_h2d(void* dst, const void* src, size_t nbytes);  /* src reusable on return */
 int tnn_d2h(void* dst, const void* src, size_t nbytes);  /* blocks until the bytes are on the host */
+/* Asynchronous read-back: copies `nbytes` of `src` into PINNED host memory on a dedicated stream,
+ * ordered after the compute work queued so far but not after anything queued later, and records
+ * `done_event` (tnn_event_create) when the bytes have landed; tnn_event_sync makes the host wait for
+ * it.  Lets a training loop log step i's loss (run.py:84 `loss.values`) while step i+1 is queued. */
+int tnn_d2h_async(void* pinned_dst, const void* src, size_t nbytes, void* done_event);
+int tnn_event_sync(void* ev);
 int tnn_d2d(void* dst, const void* src, size_t nbytes);
 int tnn_memset(void* dst, int byte, size_t nbytes);
 int tnn_host_alloc(size_t nbytes, void** out);            /* pinned host memory */

@@ -248,3 +248,22 @@ def test_failed_capture_falls_back_to_eager():
     assert np.allclose(results[0][0], results[1][0], rtol=0, atol=1e-6)
     for a, b in zip(results[0][1], results[1][1]):
         assert op_cases.rel_err(a, b) <= 1e-6
+
+
+def test_values_async_matches_values():
+    """Tensor.values_async(): the read-back runs on its own stream after the work queued so far;
+    several can be outstanding, results equal the synchronous .values (scalars and matrices)"""
+    from core.tensor import Tensor
+    rng = np.random.RandomState(3)
+    x = rng.rand(64, 33).astype(np.float32)
+    t = Tensor(x)
+    reads, want = [], []
+    for k in range(6):
+        u = t * float(k) + 1.0
+        reads.append((u.values_async(), u.sum().values_async()))
+        want.append(x * np.float32(k) + np.float32(1.0))
+        t = t + 0.0                       # more work queued behind the pending reads
+    for (rm, rs), w in zip(reads, want):
+        assert np.array_equal(rm.result(), w)
+        assert abs(float(rs.result()) - float(w.astype(np.float64).sum())) <= 1e-3 * abs(float(w.sum()))
+        assert rm.result() is rm.result()          # cached after the first wait

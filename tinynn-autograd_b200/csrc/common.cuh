@@ -17,6 +17,8 @@ struct Context {
   cudaStream_t stream = nullptr;       // compute stream: every kernel goes here
   cudaStream_t copy_stream = nullptr;  // H2D prefetch
   cudaStream_t comm_stream = nullptr;  // gradient all-reduce chunks running beside the optimiser (comm.cu)
+  cudaStream_t d2h_stream = nullptr;   // asynchronous read-backs (tnn_d2h_async): a host read of step i's
+                                       // loss must not wait for step i+1, which is already queued
   cudaEvent_t ev_comm = nullptr;       // last comm-stream fence
   cudaEvent_t ev_copy = nullptr;       // last copy-stream fence
   cudaEvent_t ev_compute = nullptr;    // last compute-stream fence

@@ -165,6 +165,7 @@ int tnn_init(int device) {
   TNN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   TNN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   TNN_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  TNN_CUDA(cudaStreamCreateWithFlags(&c.d2h_stream, cudaStreamNonBlocking));
   TNN_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
   TNN_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
   TNN_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
@@ -178,6 +179,7 @@ int tnn_shutdown(void) {
   cudaStreamSynchronize(c.stream);
   cudaStreamSynchronize(c.copy_stream);
   cudaStreamSynchronize(c.comm_stream);
+  cudaStreamSynchronize(c.d2h_stream);
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     for (auto& kv : g_pool.owned) cudaFree(kv.first);
@@ -199,6 +201,7 @@ int tnn_shutdown(void) {
   cudaStreamDestroy(c.copy_stream);
   cudaEventDestroy(c.ev_comm);
   cudaStreamDestroy(c.comm_stream);
+  cudaStreamDestroy(c.d2h_stream);
   c.inited = false;
   return 0;
 }
@@ -345,6 +348,24 @@ int tnn_d2h(void* dst, const void* src, size_t nbytes) {
   if (g_capture) TNN_FAIL("tnn_d2h: host read-back inside a graph capture (nothing has run yet)");
   TNN_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
   TNN_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int tnn_d2h_async(void* pinned_dst, const void* src, size_t nbytes, void* done_event) {
+  TNN_REQUIRE_INIT();
+  if (g_capture) TNN_FAIL("tnn_d2h_async: host read-back inside a graph capture (nothing has run yet)");
+  Context& c = ctx();
+  // ordered after what is queued on the compute stream NOW; later compute work does not delay it
+  TNN_CUDA(cudaEventRecord((cudaEvent_t)done_event, c.stream));
+  TNN_CUDA(cudaStreamWaitEvent(c.d2h_stream, (cudaEvent_t)done_event, 0));
+  if (nbytes) TNN_CUDA(cudaMemcpyAsync(pinned_dst, src, nbytes, cudaMemcpyDeviceToHost, c.d2h_stream));
+  TNN_CUDA(cudaEventRecord((cudaEvent_t)done_event, c.d2h_stream));
+  return 0;
+}
+
+int tnn_event_sync(void* ev) {
+  TNN_REQUIRE_INIT();
+  TNN_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
   return 0;
 }
 
