@@ -400,6 +400,68 @@ def test_train_step_takes_gathered_batches_directly():
         assert np.array_equal(a, b)
 
 
+def test_prefetch_iterator_integer_labels_become_one_hot_on_device():
+    """PrefetchIterator(num_classes=C): targets are the integer label vector; the batches carry the
+    dense one-hot rows `np.eye(C)[labels]` (run.py:27-28) built by tnn_one_hot, for class counts that
+    are and are not multiples of 4, shuffled and not, short last batch included"""
+    from utils.data_iterator import PrefetchIterator
+    rng = np.random.RandomState(1)
+    for C in (10, 4096, 7):
+        n = 300
+        x = rng.rand(n, 12).astype(np.float32)
+        lab = rng.randint(0, C, n)
+        got = [(b.inputs.values.copy(), b.targets.values.copy())
+               for b in PrefetchIterator(batch_size=128, num_classes=C)(x, lab)]
+        assert [len(a) for a, _ in got] == [128, 128, 44]
+        assert np.array_equal(np.concatenate([a for a, _ in got]), x)
+        assert np.array_equal(np.concatenate([b for _, b in got]), np.eye(C, dtype=np.float32)[lab])
+        np.random.seed(3)
+        got = [(b.inputs.values.copy(), b.targets.values.copy())
+               for b in PrefetchIterator(batch_size=128, shuffle=True, num_classes=C)(x, lab)]
+        np.random.seed(3)
+        order = np.arange(n)
+        np.random.shuffle(order)
+        assert np.array_equal(np.concatenate([a for a, _ in got]), x[order])
+        assert np.array_equal(np.concatenate([b for _, b in got]), np.eye(C, dtype=np.float32)[lab[order]])
+    with pytest.raises(ValueError):
+        next(iter(PrefetchIterator(batch_size=8, num_classes=3)(x, np.eye(3)[lab % 3])))
+
+
+def test_one_hot_kernel_edge_cases():
+    """tnn_one_hot: float32 / float64 outputs, labels outside [0, C) give all-zero rows"""
+    import core._backend as be
+    lab = np.array([0, 3, 2, -1, 4, 7, 1], dtype=np.int32)
+    dl = be.from_numpy(lab.view(np.float32))           # raw 4-byte device vector
+    for dt, C in ((be.F32, 4), (be.F32, 5), (be.F64, 4)):
+        out = be.empty((len(lab), C), dt)
+        be.one_hot_into(out, dl.ptr, len(lab), C)
+        want = np.zeros((len(lab), C))
+        for r, v in enumerate(lab):
+            if 0 <= v < C:
+                want[r, v] = 1.0
+        assert np.array_equal(out.numpy(), want.astype(out.numpy().dtype))
+
+
+def test_split_column_reduction_is_deterministic_and_exact_on_integers():
+    """the one-launch split column reduction (last CTA folds the partials in split order): integer
+    data sums exactly whatever the split, repeated launches are bit-identical, max / min take the
+    same path"""
+    import core._backend as be
+    rng = np.random.RandomState(2)
+    for R_, C_ in ((20000, 1024), (4099, 260), (70000, 33)):
+        a = rng.randint(-8, 9, (R_, C_)).astype(np.float32)
+        d = be.from_numpy(a)
+        s1 = be.colsum(d).numpy()
+        s2 = be.colsum(d).numpy()
+        assert np.array_equal(s1, s2)
+        assert np.array_equal(s1, a.sum(axis=0, keepdims=True, dtype=np.float64).astype(np.float32))
+        assert np.array_equal(be.reduce(be.RED_MAX, d, axis=0).numpy(), a.max(axis=0))
+        assert np.array_equal(be.reduce(be.RED_MIN, d, axis=0).numpy(), a.min(axis=0))
+    x = rng.standard_normal((30000, 512)).astype(np.float32)
+    got = be.colsum(be.from_numpy(x)).numpy()
+    assert op_cases.rel_err(got, x.astype(np.float64).sum(axis=0, keepdims=True)) <= 1e-5
+
+
 def test_predict_builds_no_graph_and_matches_forward():
     """Model.predict / ops.no_grad: same values as forward(), no autograd graph, training unaffected"""
     import core.ops as ops

@@ -237,3 +237,61 @@ def test_coverage_document_cites_existing_tests_and_files():
         assert "def %s(" % name in sources, name
     for prof in sorted(set(re.findall(r"`((?:r01[a-z]_|gemm_)[A-Za-z0-9_.]+\.(?:jsonl|json|md|log))`", text))):
         assert os.path.exists(os.path.join(ROOT, "profiles", prof)), prof
+
+
+def test_bench_arms_print_the_same_config_and_a_fixed_cpu_sample():
+    """bench.py: the B200 arm and the reference arm describe the workload with the same `config`
+    object, key for key (the driver compares them), and the CPU arm's sample size is a constant of the
+    workload -- it does not depend on --steps"""
+    sys.path.insert(0, ROOT)
+    import bench
+    for cfg, world in ((bench.WIDE, 1), (bench.WIDE, 8), (bench.MNIST, 1)):
+        a = bench.make_config(dict(cfg), cfg["batch"], world)
+        b = bench.make_config(dict(cfg), cfg["batch"], world)
+        assert a == b and a["global_batch"] == cfg["batch"] * world
+        assert a["cpu_reference_sample"] == "%d rows per step" % bench.ref_sample_batch(cfg)
+    assert bench.ref_sample_batch(bench.WIDE) == 1024 and bench.ref_sample_batch(bench.MNIST) == 128
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "pick_reference_sample" not in src           # the steps-dependent sample size of r01 is gone
+    assert bench.gemm_flops_per_step(bench.WIDE, 8192) == 11 * 2 * 8192 * 4096 * 4096
+
+
+def test_reference_arm_runs_on_cpu_and_reports_its_sample():
+    """`bench.py --impl reference` on the MNIST workload (fast): one JSON line with impl, the shared
+    config, a cpu_baseline describing the run, and the zero-copy e2e object the contract asks for"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--workload", "mnist", "--steps", "3", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["steps"] == 3 and line["config"]["workload"].startswith("mnist_mlp")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "128 of its 128 rows" in line["cpu_baseline"]["sample"]
+
+
+def test_numa_binding_helpers():
+    sys.path.insert(0, ROOT)
+    import core._dist as dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("") == set()
+    # no GPU / no sysfs entry here: nothing is changed and nothing raises
+    before = os.sched_getaffinity(0)
+    assert dist.bind_to_local_numa_node(0) is None or isinstance(dist.bind_to_local_numa_node(0), str)
+    assert os.sched_getaffinity(0) == before
+
+
+def test_reference_format_checkpoint_unpickles_without_a_gpu():
+    """the fixture written by the reference's Model.save: unpickling needs no device, and the arrays
+    come out of the reference's own attribute names"""
+    import pickle
+    sys.path.insert(0, ROOT)
+    from core.model import _pickled_values
+    with open(os.path.join(ROOT, "tests", "golden", "ref_checkpoint.pkl"), "rb") as f:
+        net = pickle.load(f)
+    shapes = [tuple(_pickled_values(layer.params[k]).shape) for layer in net.layers
+              for k in ("w", "b") if getattr(layer, "params", None)]
+    assert shapes == [(4, 3), (1, 3), (3, 2), (1, 2)]
