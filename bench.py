@@ -517,9 +517,12 @@ def run_b200_arm(args, cfg):
         per_launch_flops = flops_step * args.steps / gemm_n
         achieved = per_launch_flops / (gemm_ms / gemm_n * 1e-3) / 1e12
         # tensor-pipe cost of one algorithmic MMA, in bf16-MMA equivalents (a TF32 MMA costs two):
-        #   mix    : 1 TF32 + 2 BF16 = 4        tf32x3 : 3 TF32 = 6
+        #   f16 : 3 F16 = 3      mix : 1 TF32 + 2 BF16 = 4        tf32x3 : 3 TF32 = 6
         mix = be.TC_SPLIT == "mix"
-        cost = 4.0 if mix else 6.0
+        cost = {"f16": 3.0, "mix": 4.0}.get(be.TC_SPLIT, 6.0)
+        split_desc = {"f16": "3 F16 MMAs per algorithmic MMA (scaled fp16 hi/lo planes)",
+                      "mix": "1 TF32 + 2 BF16 MMAs per algorithmic MMA"}.get(
+                          be.TC_SPLIT, "3 TF32 MMAs per algorithmic MMA")
         peak = peaks["bf16_sustained"] / cost
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -529,12 +532,12 @@ def run_b200_arm(args, cfg):
                     "frac": achieved / peak, "traffic": traffic,
                     "frac_of_burst": achieved / (peaks["bf16_burst"] / cost),
                     "frac_of_nominal": achieved / (2250.0 / cost),
-                    "kernel": "gemm_tf32x3_kernel<MIX=%d>" % int(mix), "launches": int(gemm_n),
+                    "kernel": ("gemm_f16x3_kernel" if be.TC_SPLIT == "f16"
+                               else "gemm_tf32x3_kernel<MIX=%d>" % int(mix)), "launches": int(gemm_n),
                     "avg_launch_ms": gemm_ms / gemm_n, "share_of_step": gemm_ms / ms,
                     "split": be.TC_SPLIT,
                     "peak_source": "%s bf16 sustained %.1f TFLOP/s / %d (%s)" % (
-                        peaks["source"], peaks["bf16_sustained"], int(cost),
-                        "1 TF32 + 2 BF16 MMAs per algorithmic MMA" if mix else "3 TF32 MMAs per algorithmic MMA")}
+                        peaks["source"], peaks["bf16_sustained"], int(cost), split_desc)}
 
     # ---- the extra measurements ------------------------------------------------------------------
     arena_elems = stepper.model._arena["p"].size if stepper.model._arena else 0
@@ -561,7 +564,8 @@ def run_b200_arm(args, cfg):
             "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None,
             "dtype": "f32 (tensor-core GEMMs: %s, fp32 accumulate)" % (
-                "tf32 main term + bf16 cross terms" if be.TC_SPLIT == "mix" else "3xTF32"),
+                {"f16": "3-term split on scaled fp16 hi/lo planes", "mix": "tf32 main term + bf16 cross terms"}.get(
+                    be.TC_SPLIT, "3xTF32")),
             "data": "synthetic",
             "config": make_config(cfg, B, world),
             "step_mode": "cuda_graph_replay" if use_graph else "eager_launches",

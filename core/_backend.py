@@ -103,6 +103,15 @@ _SIGNATURES = {
     "tnn_gemm_tf32_bf16x2": [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64,
                              _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                              _c_i64, _c_vp],
+    "tnn_f16_stats": [_c_vp, _c_i64, _c_vp, _c_int],
+    "tnn_f16_meta_reset": [_c_vp],
+    "tnn_split_f16": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
+    "tnn_gemm_f16x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64,
+                       _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
+    "tnn_split_tf32_bf16_cond": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_int,
+                                 _c_vp],
+    "tnn_gemm_tf32_bf16x2_cond": [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64,
+                                  _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "tnn_set_gemm_cta_group": [_c_int],
     "tnn_set_gemm_ksplit": [_c_int],
     "tnn_set_gemm_group_m": [_c_int],
@@ -749,7 +758,9 @@ TC_ENABLED = os.environ.get("TNN_TC", "1") != "0"
 TC_MN_MAJOR = os.environ.get("TNN_TC_MN_MAJOR", "1") != "0"   # 0: transposed tf32 planes instead
 # operand split of the tensor-core product: "mix" = tf32 main term + bf16 cross terms (default),
 # "tf32x3" = three tf32 MMAs per K step (the textbook 3xTF32, kept as cross-check)
-TC_SPLIT = os.environ.get("TNN_GEMM_SPLIT", "mix")
+# "f16" (default) = scaled fp16 + bf16 planes, three kind::f16 MMAs (gemm_f16.cu), with the mixed
+# split as on-device fallback for operands outside its guard;
+TC_SPLIT = os.environ.get("TNN_GEMM_SPLIT", "f16")
 # fused Dense+ReLU launch on the tensor-core path: do not write the fp32 activation (see LazyReLU)
 LAZY_RELU_OUT = os.environ.get("TNN_LAZY_RELU", "1") != "0"
 BF16_BYTES = 2
@@ -790,6 +801,102 @@ def split_planes_mix(x):
         _raise("tnn_split_tf32_bf16")
     cache["m"] = (hi, h16, l16, ld)
     return cache["m"]
+
+
+def _new_meta():
+    """32-byte operand record of the f16 split (gemm_f16.cu: Meta)"""
+    return empty((8,), F32)
+
+
+def split_planes_f16(x):
+    """fp32 (R, C) -> (hf fp16 plane, l16 bf16 plane, ld, meta, source array, relu_mode), cached for
+    the step.  A LazyReLU is split straight from its pre-activation (relu applied on load); the
+    statistics come from the producer's epilogue when it left a record (cache["stat"])."""
+    cache = x.split
+    if cache is None or cache.get("epoch") != _split_epoch:
+        cache = {"epoch": _split_epoch}
+        x.split = cache
+    if "f" in cache:
+        return cache["f"]
+    R, C = x.shape
+    ld = _round8(C)
+    if type(x) is LazyReLU and x._real is None:
+        src, relu_mode = x._src, 1
+    else:
+        src, relu_mode = x, 0
+    meta = cache.get("stat")
+    if meta is None:
+        meta = _new_meta()
+        if _lib.tnn_f16_stats(src.ptr, R * C, meta.ptr, relu_mode):
+            _raise("tnn_f16_stats")
+    hf, l16 = _empty_bf16(R, ld), _empty_bf16(R, ld)
+    if _lib.tnn_split_f16(src.ptr, R, C, hf.ptr, l16.ptr, ld, meta.ptr, relu_mode):
+        _raise("tnn_split_f16")
+    # (the source is not stored when it is x itself: x -> x.split -> x would be a reference cycle,
+    # and blocks held by cycles are only returned to the pool by the garbage collector)
+    cache["f"] = (hf, l16, ld, meta, src if src is not x else None, relu_mode)
+    return cache["f"]
+
+
+_FALLBACK_PLANES = {}
+
+
+def _fallback_planes(role, R, ld):
+    """scratch for the conditional mixed split behind an f16 product (stream-ordered reuse)"""
+    key = (role, R, ld)
+    p = _FALLBACK_PLANES.get(key)
+    if p is None:
+        if len(_FALLBACK_PLANES) >= 16:
+            _FALLBACK_PLANES.clear()
+        p = (empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld))
+        _FALLBACK_PLANES[key] = p
+    return p
+
+
+def _matmul_f16(a, b, ta, tb, bias, out, flags, act, mask_src, M, N, K):
+    a_hf, a_l16, lda, a_meta, a_src, a_relu = split_planes_f16(a)
+    b_hf, b_l16, ldb, b_meta, b_src, b_relu = split_planes_f16(b)
+    a_src = a if a_src is None else a_src
+    b_src = b if b_src is None else b_src
+    layout = (1 if ta else 0) | (0 if tb else 2)
+    act_out = None
+    stat = None
+    if act:
+        stat = _new_meta()
+        if _lib.tnn_f16_meta_reset(stat.ptr):
+            _raise("tnn_f16_meta_reset")
+        if mask_src is None and LAZY_RELU_OUT:
+            act_out = LazyReLU(out)          # statistics only: the fp32 activation is not written
+            flags |= 8
+        else:
+            act_out = empty((M, N), F32)
+    real_act = act_out if (act and type(act_out) is not LazyReLU) else None
+    bias_p = bias.ptr if bias is not None else None
+    mask_p = mask_src.ptr if (act and mask_src is not None) else None
+    if _lib.tnn_gemm_f16x3(out.ptr, N, a_hf.ptr, a_l16.ptr, lda, a_meta.ptr, b_hf.ptr, b_l16.ptr, ldb,
+                           b_meta.ptr, M, N, K, bias_p, flags, layout,
+                           real_act.ptr if real_act is not None else None, mask_p,
+                           stat.ptr if stat is not None else None):
+        _raise("tnn_gemm_f16x3")
+    # on-device fallback: these three launches return at once when both operands were inside the guard
+    fa = _fallback_planes(0, a.shape[0], lda)
+    fb = _fallback_planes(1, b.shape[0], ldb)
+    if _lib.tnn_split_tf32_bf16_cond(a_src.ptr, a.shape[0], a.shape[1], fa[0].ptr, fa[1].ptr, fa[2].ptr, lda,
+                                     a_meta.ptr, b_meta.ptr, a_relu,
+                                     stat.ptr if stat is not None else None):
+        _raise("tnn_split_tf32_bf16_cond")
+    if _lib.tnn_split_tf32_bf16_cond(b_src.ptr, b.shape[0], b.shape[1], fb[0].ptr, fb[1].ptr, fb[2].ptr, ldb,
+                                     a_meta.ptr, b_meta.ptr, b_relu, None):
+        _raise("tnn_split_tf32_bf16_cond")
+    if _lib.tnn_gemm_tf32_bf16x2_cond(out.ptr, N, fa[0].ptr, fa[1].ptr, fa[2].ptr, lda, fb[0].ptr, fb[1].ptr,
+                                      fb[2].ptr, ldb, M, N, K, bias_p, flags & 3, layout,
+                                      real_act.ptr if real_act is not None else None, mask_p,
+                                      a_meta.ptr, b_meta.ptr):
+        _raise("tnn_gemm_tf32_bf16x2_cond")
+    if act:
+        act_out.split = {"epoch": _split_epoch, "stat": stat}
+        return out, act_out
+    return out
 
 
 def split_planes(x, transposed, also_other=False):
@@ -875,6 +982,8 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
     if M == 0 or N == 0:
         return (out, act_out) if act else out
     flags = (1 if accumulate else 0) | (2 if relu else 0)
+    if K > 0 and use_tensor_cores(M, N, K, dt) and TC_SPLIT == "f16":
+        return _matmul_f16(a, b, ta, tb, bias, out, flags, act, mask_src, M, N, K)
     if K > 0 and use_tensor_cores(M, N, K, dt) and TC_SPLIT == "mix":
         a_hi, a_h16, a_l16, lda = split_planes_mix(a)
         b_hi, b_h16, b_l16, ldb = split_planes_mix(b)

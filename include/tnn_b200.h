@@ -238,6 +238,45 @@ int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
                          int64_t M, int64_t N, int64_t K, const float* bias, int flags, int layout,
                          float* act_out, float* act_hi, void* act_h16, void* act_l16, int64_t ld_act,
                          const float* mask_src);
+/* Scaled two-plane split (the default path since r02): the 3xTF32 expansion with every factor in 16
+ * bits.  X = x * 2^e (one e per tensor: max|X| in [2^14, 2^15)), hf = fp16(X) (the mantissa tf32
+ * keeps), l = bf16(X - hf);
+ *     A*B ~= 2^-(ea+eb) * ( l_A*hf_B + hf_A*l_B + hf_A*hf_B )
+ * as three tcgen05 kind::f16 MMAs per K=16 step (f16 and bf16 operands mixed) on 4 B/element of
+ * planes.  Element error <= 2^-20 * max(|x|, 2^-28 max|X_tensor|); replaces ops.py:150-160 `@`.
+ * Each operand carries a 16-byte device record `meta` {u32 bits of max|x|, u32 ~bits of the min
+ * non-zero |x|, i32 e, i32 safe}:
+ * tnn_f16_stats      zeroes the record and fills the two statistics of x (relu_mode: of relu(x)).
+ * tnn_f16_meta_reset zeroes a record a producer kernel is about to fill (tnn_gemm_f16x3 stat_meta).
+ * tnn_split_f16      derives e and `safe` from the statistics (safe = finite, and no non-zero
+ *                    element more than 40 binades below the largest) and, when safe, writes the planes
+ *                    (pitch ld, multiple of 8, pad columns zeroed).
+ * tnn_gemm_f16x3     layout bits / flags 1, 2 as tnn_gemm_tf32x3; returns at once ON THE DEVICE
+ *                    unless both operands are safe.  act_out (optional) = relu(D), or with mask_src
+ *                    D * (mask_src >= 0) (ops.py:336-343 fused into the dX product).  stat_meta
+ *                    (optional): statistics of the result -- of act_out's values when act_out or
+ *                    mask_src is given, of relu(D) with flags & 8 -- for the split of the next product.
+ * tnn_split_tf32_bf16_cond / tnn_gemm_tf32_bf16x2_cond: the fallback for operands outside the guard,
+ *   launched unconditionally behind tnn_gemm_f16x3: they return at once when both records say safe,
+ *   otherwise split (relu_mode: relu(x)) / multiply with the mixed split above.  No host round trip.
+ *   poison_meta (optional): the record tnn_gemm_f16x3 would have filled with its result's statistics;
+ *   the fallback marks it non-finite, so the next f16 split of that result falls back as well. */
+int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode);
+int tnn_f16_meta_reset(void* meta);
+int tnn_split_f16(const float* x, int64_t R, int64_t C, void* hf, void* l16, int64_t ld, void* meta,
+                  int relu_mode);
+int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, int64_t lda,
+                   const void* a_meta, const void* b_hf, const void* b_l16, int64_t ldb,
+                   const void* b_meta, int64_t M, int64_t N, int64_t K, const float* bias, int flags,
+                   int layout, float* act_out, const float* mask_src, void* stat_meta);
+int tnn_split_tf32_bf16_cond(const float* x, int64_t R, int64_t C, float* hi, void* h16, void* l16,
+                             int64_t ld, const void* meta_a, const void* meta_b, int relu_mode,
+                             void* poison_meta);
+int tnn_gemm_tf32_bf16x2_cond(float* D, int64_t ldd, const float* a_hi, const void* a_h16,
+                              const void* a_l16, int64_t lda, const float* b_hi, const void* b_h16,
+                              const void* b_l16, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                              const float* bias, int flags, int layout, float* act_out,
+                              const float* mask_src, const void* meta_a, const void* meta_b);
 /* CTA-group size of the tcgen05 kernel: 1 = one CTA per SM (tile 128x256), 2 = CTA pair with
  * cta_group::2 (tile 256x256), 0 = library default.  Also settable with TNN_GEMM_CG. */
 int tnn_set_gemm_cta_group(int cg);

@@ -1,0 +1,747 @@
+// Tensor-core GEMM for ops.py:150-163 (dot_: A@B, grad@B.T, A.T@grad), scaled two-plane fp16 split:
+//
+//     X = x * 2^e                        e per TENSOR, so that max|X| lies in [2^14, 2^15)
+//     hf = fp16(X)                       11 significant bits (the same mantissa tf32(x) keeps)
+//     l  = fp16(X - hf)                  the next 11 bits
+//     A*B ~= 2^-(ea+eb) * ( l_A*hf_B + hf_A*l_B + hf_A*hf_B )          fp32 accumulation in TMEM
+//
+// i.e. the 3xTF32 expansion with every factor held in 16 bits: 4 bytes of planes per element instead
+// of 8 and three kind::f16 MMAs per K=16 step (the tensor pipe's fastest dense fp32-accumulating
+// rate) instead of one kind::tf32 + two kind::f16.  (kind::f16 does not take an f16 and a bf16 operand
+// in one instruction -- tried, "illegal instruction" -- so both planes are fp16.)
+// Element error: |X - hf - l| <= 2^-22 |X| while the residual is a normal fp16 number (|X| >= 2^-3),
+// <= 2^-25 absolute below, i.e.
+//     err(a_ik) <= 2^-20 * max(|a_ik|, 2^-19 * max|A|)        (2^-25 <= 2^-39 max|X|)
+// -- at least the mixed tf32/bf16 split's accuracy for every element within 19 binades of the
+// tensor's largest, an absolute floor of 2^-39 max|A| (five orders below fp32's own rounding of the
+// large entries) under that; the dropped l*l term is 2^-22 relative.  That is a tensor-relative
+// bound, so the split kernel guards it ON THE DEVICE: it counts the non-zero elements below the
+// floor (|X| < 2^-5) and flags the tensor `unsafe` when they are more than 1/256 of the non-zeros
+// (rows or columns on wildly different scales, exponents spread over tens of binades) or when the
+// tensor holds NaN/Inf.  The f16 GEMM returns at once for an unsafe operand and the conditional
+// mixed-split launches that follow it (gemm_tc.cu: tnn_split_tf32_bf16_cond,
+// tnn_gemm_tf32_bf16x2_cond) do the product instead -- no host round trip, capturable in a graph.
+//
+// Kernel: same skeleton as gemm_tc.cu (persistent CTA pairs, cta_group::2, tile 256 x 256, warp 0 TMA
+// producer, warp 1 MMA issuer, warps 4-11 drain TMEM chunks into fp32 registers with RN adds), with
+// 64-wide K blocks (128-byte rows of 16-bit elements, SWIZZLE_128B both majors), 3 stages x 64 KB.
+// Algorithmic work 2*M*N*K flop per call; the tensor pipe executes 3x that at the bf16/fp16 rate;
+// operand bytes 4*(M+N)*K.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tnn {
+namespace f16 {
+
+using namespace tnn::tc;
+
+constexpr int BK = 64;                       // 16-bit elements per K block = 128-byte rows
+constexpr int ROWS = 128;                    // rows of A and rows of B staged per CTA
+constexpr int UMMA_N = 256;
+constexpr int TILE_M = 256;                  // CTA pair
+constexpr int UMMA_K = 16;
+constexpr int PLANE_BYTES = ROWS * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = 4 * PLANE_BYTES; // A.hf, A.l, B.hf, B.l
+constexpr int STAGES = 3;
+constexpr int CHUNK_KB = 4;                  // 256 k per TMEM accumulator chunk (as gemm_tc.cu)
+constexpr int NUM_THREADS = 384;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int EPI_PATCH_BYTES = 8 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_PATCH_BYTES;
+constexpr int MN_BOX_BYTES = 64 * BK * 2;    // one {64 mn, 64 k} box
+constexpr float SMALL_LIMIT = 0.03125f;      // 2^-5: below it the residual plane is subnormal
+constexpr unsigned int GUARD_FRACTION = 256; // unsafe when small non-zeros * 256 > non-zeros
+
+// per-operand device record (32 bytes).  absmax is filled by stats_kernel or a producer's epilogue;
+// the rest by split_f16_kernel.  Word 3 (`safe`) is what the conditional kernels of gemm_tc.cu read.
+struct Meta {
+  unsigned int absmax;      // bits of max |x| (NaN sorts above Inf)
+  unsigned int reserved;
+  int exp;                  // planes hold x * 2^exp
+  int safe;                 // 1: planes are valid and inside the guard
+  unsigned int n_small;     // non-zero elements with |X| < SMALL_LIMIT
+  unsigned int n_nz;        // non-zero elements
+  unsigned int ticket;      // CTAs of the split kernel that have finished
+  unsigned int pad;
+};
+
+// scale exponent from the tensor's largest magnitude; ok = 0 for NaN/Inf or a tensor so small that
+// the scale itself would overflow
+__device__ __forceinline__ void meta_scale(unsigned int amax_bits, int& e, int& ok) {
+  e = 0;
+  ok = 1;
+  if (amax_bits == 0u) return;                       // all zeros
+  if (amax_bits >= 0x7F800000u) { ok = 0; return; }
+  const int ex = (int)(amax_bits >> 23) - 127;
+  if (ex < -112) { ok = 0; return; }
+  e = 14 - ex;
+}
+
+__device__ __forceinline__ float pow2f(int e) {      // e in [-126, 127]
+  return __int_as_float((e + 127) << 23);
+}
+
+// K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart; a K=16 step advances 32 B.
+// MN-major, SWIZZLE_128B: {64 mn, 64 k} boxes of 8192 B (k-row j at j*128 B); 8-k groups 1024 B
+// apart (SBO), 64-element M/N chunks one box apart (LBO); a K=16 step advances 2048 B.
+template <bool MN>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(MN ? (MN_BOX_BYTES >> 4) : 1) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D = F32; a_fmt / b_fmt: 0 = F16, 1 = BF16
+__host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int b_fmt, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  tm = t / tiles_n;
+  tn = t - tm * tiles_n;
+}
+
+// flags: 1 accumulate into D, 2 ReLU in place, 8 statistics of relu(D) instead of D
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_constant__ CUtensorMap map_a_l,
+                  const __grid_constant__ CUtensorMap map_b_h, const __grid_constant__ CUtensorMap map_b_l,
+                  float* __restrict__ D, int64_t ldd, int M, int N, int K,
+                  const float* __restrict__ bias, int flags, int t_full, int tail_split,
+                  unsigned int* __restrict__ tile_flags, float* __restrict__ act_out,
+                  const float* __restrict__ mask_src, const Meta* __restrict__ meta_a,
+                  const Meta* __restrict__ meta_b, Meta* __restrict__ stat_out) {
+  // operands outside the guard: the conditional mixed-split launches behind this one take over
+  if (!(meta_a->safe && meta_b->safe)) return;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_h);
+    tma_prefetch_desc(&map_a_l);
+    tma_prefetch_desc(&map_b_h);
+    tma_prefetch_desc(&map_b_l);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 16);   // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<2>(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int tiles_m = (M + TILE_M - 1) / TILE_M;
+  const int tiles_n = (N + UMMA_N - 1) / UMMA_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int group = blockIdx.x / 2;
+  const int num_groups = gridDim.x / 2;
+  // work units: whole-K tiles [0, t_full), then the ragged last wave cut into tail_split K ranges
+  // (fixed-order read-modify-write behind a per-tile arrival counter, see gemm_tc.cu)
+  const int tail_rem = num_tiles - t_full;
+  const int num_units = t_full + tail_rem * tail_split;
+  const int kb_per_split = (num_kb + tail_split - 1) / tail_split;
+  auto decode = [&](int u, int& t, int& sp, int& kb_begin, int& kb_end) {
+    if (u < t_full) {
+      t = u; sp = 0; kb_begin = 0; kb_end = num_kb;
+    } else {
+      const int j = u - t_full;
+      t = t_full + j % tail_rem;
+      sp = j / tail_rem;
+      kb_begin = sp * kb_per_split;
+      kb_end = min(num_kb, kb_begin + kb_per_split);
+    }
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = group; u < num_units; u += num_groups) {
+        int t, sp, kb_begin, kb_end;
+        decode(u, t, sp, kb_begin, kb_end);
+        int tm, tn;
+        tile_coords(t, tiles_m, tiles_n, tm, tn);
+        const int row_a = tm * TILE_M + (int)cta_rank * ROWS;
+        const int row_b = tn * UMMA_N + (int)cta_rank * ROWS;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa_h = smem_base + stage * STAGE_BYTES;
+          const uint32_t sa_l = sa_h + PLANE_BYTES;
+          const uint32_t sb_h = sa_h + 2 * PLANE_BYTES;
+          const uint32_t sb_l = sa_h + 3 * PLANE_BYTES;
+          if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)STAGE_BYTES * 2u);
+          const int k0 = kb * BK;
+          if (flags & 128) {
+            // TIMING EXPERIMENT (TNN_EXP_FLAGS, results are wrong): no operand fetch
+            if (leader)
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full_bar(stage)), "r"((uint32_t)STAGE_BYTES * 2u) : "memory");
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < ROWS / 64; ++j) {
+              tma_load_2d<2>(sa_l + j * MN_BOX_BYTES, &map_a_l, full_bar(stage), row_a + 64 * j, k0);
+              tma_load_2d<2>(sa_h + j * MN_BOX_BYTES, &map_a_h, full_bar(stage), row_a + 64 * j, k0);
+            }
+          } else {
+            tma_load_2d<2>(sa_l, &map_a_l, full_bar(stage), k0, row_a);
+            tma_load_2d<2>(sa_h, &map_a_h, full_bar(stage), k0, row_a);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int j = 0; j < ROWS / 64; ++j) {
+              tma_load_2d<2>(sb_h + j * MN_BOX_BYTES, &map_b_h, full_bar(stage), row_b + 64 * j, k0);
+              tma_load_2d<2>(sb_l + j * MN_BOX_BYTES, &map_b_l, full_bar(stage), row_b + 64 * j, k0);
+            }
+          } else {
+            tma_load_2d<2>(sb_h, &map_b_h, full_bar(stage), k0, row_b);
+            tma_load_2d<2>(sb_l, &map_b_l, full_bar(stage), k0, row_b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(0, 0, A_MN, B_MN);      // f16 x f16 -> f32
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = group; u < num_units; u += num_groups) {
+        int t, sp, kb_begin, kb_end;
+        decode(u, t, sp, kb_begin, kb_end);
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
+          const int kb1 = min(kb0 + CHUNK_KB, kb_end);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa_h = smem_base + stage * STAGE_BYTES;
+            const uint32_t sa_l = sa_h + PLANE_BYTES;
+            const uint32_t sb_h = sa_h + 2 * PLANE_BYTES;
+            const uint32_t sb_l = sa_h + 3 * PLANE_BYTES;
+            if (!(flags & 256))   // (256: timing experiment, no MMA issued)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff_a = (uint32_t)(k * (A_MN ? 2048 : 32));
+              const uint32_t koff_b = (uint32_t)(k * (B_MN ? 2048 : 32));
+              const uint64_t da_h = make_desc<A_MN>(sa_h + koff_a);
+              const uint64_t da_l = make_desc<A_MN>(sa_l + koff_a);
+              const uint64_t db_h = make_desc<B_MN>(sb_h + koff_b);
+              const uint64_t db_l = make_desc<B_MN>(sb_l + koff_b);
+              // small terms first; the first MMA of a chunk overwrites the accumulator
+              umma_bf16<2>(tmem_d, da_l, db_h, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              umma_bf16<2>(tmem_d, da_h, db_l, idesc, 1u);
+              umma_bf16<2>(tmem_d, da_h, db_h, idesc, 1u);
+            }
+            umma_commit<2>(empty_bar(stage));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit<2>(tfull_bar(acc));
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    // ================= epilogue =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool relu = flags & 2;
+    // 2^-(ea+eb) as two factors (each a normal float; the intermediate lies between the scaled
+    // sum and the result, so it cannot overflow or underflow unless the result does)
+    const int ec = -(meta_a->exp + meta_b->exp);
+    const float f1 = pow2f(ec / 2), f2 = pow2f(ec - ec / 2);
+    unsigned int st_max = 0u;
+    for (int u = group; u < num_units; u += num_groups) {
+      int t, sp, kb_begin, kb_end;
+      decode(u, t, sp, kb_begin, kb_end);
+      const bool accumulate = (flags & 1) || sp > 0;
+      const bool final_unit = (u < t_full || sp + 1 == tail_split);
+      const bool emit_act = act_out != nullptr && final_unit;
+      const bool want_stats = stat_out != nullptr && final_unit;
+      const float* bias_u = sp == 0 ? bias : nullptr;
+      int tm, tn;
+      tile_coords(t, tiles_m, tiles_n, tm, tn);
+      const int col0 = tn * UMMA_N + half * 128;
+      float sum[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                               (uint32_t)(acc * UMMA_N + half * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if (sp > 0) {
+        if (lane == 0) {
+          const unsigned int need = (unsigned int)(sp * 16);
+          unsigned int seen;
+          long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tile_flags + t) : "memory");
+            if (clock64() - t0 > 8000000000LL) {
+              printf("tnn gemm_f16: split-K ordering wait timed out (tile %d split %d)\n", t, sp);
+              __trap();
+            }
+          } while (seen < need);
+        }
+        __syncwarp();
+        __threadfence();
+      }
+      {
+        const int row_base = tm * TILE_M + (int)cta_rank * ROWS + quad * 32;
+        float4* patch = reinterpret_cast<float4*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
+        const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+        const bool act_aligned = !emit_act || (((reinterpret_cast<uintptr_t>(act_out) |
+                                                  reinterpret_cast<uintptr_t>(mask_src)) & 15) == 0);
+        const bool fast_rows = rows_aligned && act_aligned;
+        const bool want_mask = emit_act && mask_src != nullptr;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          const int colb = col0 + cb * 32;
+          if (colb >= N) break;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 v = make_float4(sum[cb * 32 + c4 * 4] * f1 * f2, sum[cb * 32 + c4 * 4 + 1] * f1 * f2,
+                                   sum[cb * 32 + c4 * 4 + 2] * f1 * f2, sum[cb * 32 + c4 * 4 + 3] * f1 * f2);
+            if (bias_u) {
+              const int c = colb + c4 * 4;
+              if (c + 3 < N) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_u + c);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              } else {
+                if (c < N) v.x += bias_u[c];
+                if (c + 1 < N) v.y += bias_u[c + 1];
+                if (c + 2 < N) v.z += bias_u[c + 2];
+              }
+            }
+            patch[lane * 8 + (c4 ^ (lane & 7))] = v;
+          }
+          __syncwarp();
+          const float* pre_src = accumulate ? D : (want_mask ? mask_src : nullptr);
+          float4 pre[8];
+          if (fast_rows && pre_src != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int grow = row_base + 4 * i + (lane >> 3), gcol = colb + (lane & 7) * 4;
+              if (grow < M && gcol + 3 < N)
+                pre[i] = *reinterpret_cast<const float4*>(pre_src + (int64_t)grow * ldd + gcol);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3), c4 = lane & 7;
+            float4 v = patch[r * 8 + (c4 ^ (r & 7))];
+            const int grow = row_base + r, gcol = colb + c4 * 4;
+            if (grow < M && gcol < N) {
+              float* dp = D + (int64_t)grow * ldd + gcol;
+              float e[4];
+              const int nvalid = min(4, N - gcol);
+              if (nvalid == 4 && fast_rows) {
+                if (accumulate) {
+                  const float4 o = pre[i];
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                if (relu) {
+                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                  v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(dp) = v;
+                e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+                if (want_mask) {
+                  // act = D * (pre-activation >= 0): the ReLU gradient mask of ops.py:336-343
+                  const float4 z = accumulate
+                      ? *reinterpret_cast<const float4*>(mask_src + (int64_t)grow * ldd + gcol)
+                      : pre[i];
+                  e[0] = z.x >= 0.f ? v.x : v.x * 0.f; e[1] = z.y >= 0.f ? v.y : v.y * 0.f;
+                  e[2] = z.z >= 0.f ? v.z : v.z * 0.f; e[3] = z.w >= 0.f ? v.w : v.w * 0.f;
+                } else if (emit_act || (flags & 8)) {
+                  // ReLU(D), NaN-propagating like np.clip
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) e[k] = e[k] < 0.f ? 0.f : e[k];
+                }
+                if (emit_act)
+                  *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = make_float4(e[0], e[1], e[2], e[3]);
+              } else {
+                const float s[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  e[k] = 0.f;
+                  if (k < nvalid) {
+                    float x = s[k];
+                    if (accumulate) x += dp[k];
+                    if (relu) x = fmaxf(x, 0.f);
+                    dp[k] = x;
+                    float a = x;
+                    if (want_mask) a = mask_src[(int64_t)grow * ldd + gcol + k] >= 0.f ? x : x * 0.f;
+                    else if (emit_act || (flags & 8)) a = x < 0.f ? 0.f : x;
+                    if (emit_act) act_out[(int64_t)grow * ldd + gcol + k] = a;
+                    e[k] = a;
+                  }
+                }
+              }
+              if (want_stats) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  st_max = max(st_max, __float_as_uint(e[k]) & 0x7FFFFFFFu);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (u >= t_full && sp + 1 < tail_split) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(tile_flags + t, 1u);
+      }
+    }
+    if (stat_out != nullptr) {
+      // integer max is exact and order-independent: the record does not depend on timing
+      st_max = __reduce_max_sync(0xFFFFFFFFu, st_max);
+      if (lane == 0 && st_max) atomicMax(&stat_out->absmax, st_max);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- statistics + split ---------------------------------------------------------------------------
+
+// max |x| of (relu_mode ? relu(x) : x) over n elements -> meta->absmax (integer atomicMax)
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ x, int64_t n, Meta* __restrict__ meta, int relu_mode, int vec) {
+  unsigned int mx = 0u;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto take = [&](float v) {
+    if (relu_mode && v < 0.f) v = 0.f;
+    mx = max(mx, __float_as_uint(v) & 0x7FFFFFFFu);
+  };
+  if (vec) {
+    const int64_t n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 t = x4[i];
+      take(t.x); take(t.y); take(t.z); take(t.w);
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) take(x[i]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) take(x[i]);
+  }
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  __shared__ unsigned int s_mx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_mx[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = max(mx, s_mx[w]);
+    if (mx) atomicMax(&meta->absmax, mx);
+  }
+}
+
+// x [R, C] (relu_mode: relu(x)) -> hf = fp16(x 2^e), l = fp16(x 2^e - hf), pitch ld (multiple of 8,
+// pad columns zeroed); e is derived from meta->absmax by every thread.  While writing, the kernel
+// counts non-zero and "small" elements (integer atomics: order-independent); the last CTA to finish
+// turns the counts into the `safe` flag.  8 B written per 4 B read.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, int64_t R, int64_t C, __half* __restrict__ hf,
+                 __half* __restrict__ l16, int64_t ld, Meta* __restrict__ meta, int relu_mode,
+                 int vec_in) {
+  int e, ok;
+  meta_scale(meta->absmax, e, ok);
+  const float sc = ok ? pow2f(e) : 1.f;
+  const int64_t gpr = ld / 8;
+  const int64_t total = R * gpr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned int n_small = 0u, n_nz = 0u;
+  if (ok) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const int64_t r = i / gpr, c = (i - r * gpr) * 8;
+      float v[8];
+      if (vec_in && c + 7 < C) {
+        const float4 t0 = *reinterpret_cast<const float4*>(x + r * C + c);
+        const float4 t1 = *reinterpret_cast<const float4*>(x + r * C + c + 4);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+        v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (c + k < C) ? x[r * C + c + k] : 0.f;
+      }
+      union { __half2 h[4]; uint4 u; } ph, pl;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = v[2 * k], b = v[2 * k + 1];
+        if (relu_mode) { a = a < 0.f ? 0.f : a; b = b < 0.f ? 0.f : b; }
+        a *= sc; b *= sc;
+        n_nz += (a != 0.f) + (b != 0.f);
+        n_small += (a != 0.f && fabsf(a) < SMALL_LIMIT) + (b != 0.f && fabsf(b) < SMALL_LIMIT);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hb = __half22float2(h);
+        ph.h[k] = h;
+        pl.h[k] = __floats2half2_rn(a - hb.x, b - hb.y);
+      }
+      *reinterpret_cast<uint4*>(hf + r * ld + c) = ph.u;
+      *reinterpret_cast<uint4*>(l16 + r * ld + c) = pl.u;
+    }
+  }
+  n_small = __reduce_add_sync(0xFFFFFFFFu, n_small);
+  n_nz = __reduce_add_sync(0xFFFFFFFFu, n_nz);
+  __shared__ unsigned int s_small[8], s_nz[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_small[warp] = n_small; s_nz[warp] = n_nz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { n_small += s_small[w]; n_nz += s_nz[w]; }
+    if (n_small) atomicAdd(&meta->n_small, n_small);
+    if (n_nz) atomicAdd(&meta->n_nz, n_nz);
+    __threadfence();
+    if (atomicAdd(&meta->ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned int ts = *reinterpret_cast<volatile unsigned int*>(&meta->n_small);
+      const unsigned int tn = *reinterpret_cast<volatile unsigned int*>(&meta->n_nz);
+      meta->exp = e;
+      meta->safe = (ok && (unsigned long long)ts * GUARD_FRACTION <= (unsigned long long)tn) ? 1 : 0;
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  TNN_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) TNN_FAIL("cuTensorMapEncodeTiled is not available");
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return 0;
+}
+
+// 16-bit plane.  K-major [rows, K] (pitch ld): box {64 k, 128 rows}.  MN-major [K, rows] (pitch
+// ld): box {64 mn, 64 k}.  128-byte swizzle both ways.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld,
+                    bool mn_major) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) TNN_FAIL("f16 GEMM: operand plane must be 16-byte aligned");
+  if (ld % 8 != 0) TNN_FAIL("f16 GEMM: operand pitch must be a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)(mn_major ? BK : ROWS)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) TNN_FAIL("cuTensorMapEncodeTiled (f16 planes) failed with code " + std::to_string((int)r));
+  return 0;
+}
+
+static unsigned int* g_tile_flags = nullptr;
+constexpr int MAX_FLAG_TILES = 1 << 16;
+static bool g_attr_set[2][2] = {};
+
+template <bool A_MN, bool B_MN>
+static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64_t lda, const void* b_h,
+                  const void* b_l, int64_t ldb, int64_t M, int64_t N, int64_t K, const float* bias,
+                  int flags, float* act_out, const float* mask_src, const Meta* meta_a,
+                  const Meta* meta_b, Meta* stat_out) {
+  CUtensorMap ma_h, ma_l, mb_h, mb_l;
+  if (make_map(&ma_h, a_h, M, K, lda, A_MN)) return 1;
+  if (make_map(&ma_l, a_l, M, K, lda, A_MN)) return 1;
+  if (make_map(&mb_h, b_h, N, K, ldb, B_MN)) return 1;
+  if (make_map(&mb_l, b_l, N, K, ldb, B_MN)) return 1;
+  auto kern = gemm_f16x3_kernel<A_MN, B_MN>;
+  if (!g_attr_set[A_MN][B_MN]) {
+    TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    g_attr_set[A_MN][B_MN] = true;
+  }
+  const int64_t tiles = ceil_div(M, TILE_M) * ceil_div(N, UMMA_N);
+  const int max_groups = std::max(1, ctx().sm_count / 2);
+  int t_full = (int)tiles, tail_split = 1;
+  if (!(flags & 2) && tiles <= MAX_FLAG_TILES) {
+    const int64_t num_kb = ceil_div(K, BK);
+    const int64_t rem = tiles % max_groups;
+    if (rem > 0) {
+      int s = 1;
+      while (s < 4 && rem * (s * 2) <= max_groups && num_kb / (s * 2) >= 8) s *= 2;
+      if (s > 1) {
+        t_full = (int)(tiles - rem);
+        tail_split = s;
+      }
+    }
+  }
+  if (tail_split > 1) {
+    if (!g_tile_flags) TNN_CUDA(cudaMalloc(&g_tile_flags, MAX_FLAG_TILES * sizeof(unsigned int)));
+    TNN_CUDA(cudaMemsetAsync(g_tile_flags, 0, (size_t)tiles * sizeof(unsigned int), ctx().stream));
+  }
+  const int64_t units = t_full + (tiles - t_full) * tail_split;
+  const int groups = (int)std::min<int64_t>(units, max_groups);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * 2));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = ctx().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_begin(1);
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_h, ma_l, mb_h, mb_l, D, ldd, (int)M, (int)N, (int)K, bias, flags,
+                              t_full, tail_split, g_tile_flags, act_out, mask_src, meta_a, meta_b, stat_out));
+  ctx().launches++;
+  prof_end(1);
+  return 0;
+}
+
+}  // namespace f16
+}  // namespace tnn
+
+using namespace tnn;
+
+extern "C" {
+
+int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode) {
+  TNN_REQUIRE_INIT();
+  if (!meta) TNN_FAIL("tnn_f16_stats: meta is required");
+  TNN_CUDA(cudaMemsetAsync(meta, 0, sizeof(f16::Meta), ctx().stream));
+  if (n <= 0) return 0;
+  const int vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  prof_begin(3);
+  f16::stats_kernel<<<ew_grid(ceil_div(n, 16), 256), 256, 0, ctx().stream>>>(x, n, (f16::Meta*)meta, relu_mode, vec);
+  TNN_POST_LAUNCH();
+  prof_end(3);
+  return 0;
+}
+
+int tnn_f16_meta_reset(void* meta) {
+  TNN_REQUIRE_INIT();
+  if (!meta) TNN_FAIL("tnn_f16_meta_reset: meta is required");
+  TNN_CUDA(cudaMemsetAsync(meta, 0, sizeof(f16::Meta), ctx().stream));
+  return 0;
+}
+
+int tnn_split_f16(const float* x, int64_t R, int64_t C, void* hf, void* l16, int64_t ld, void* meta,
+                  int relu_mode) {
+  TNN_REQUIRE_INIT();
+  if (R <= 0 || C <= 0) return 0;
+  if (!hf || !l16 || !meta) TNN_FAIL("tnn_split_f16: both planes and the meta record are required");
+  if (ld % 8 != 0 || ld < C) TNN_FAIL("tnn_split_f16: ld must be >= C and a multiple of 8");
+  const int vec_in = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  prof_begin(3);
+  f16::split_f16_kernel<<<ew_grid(R * (ld / 8), 256), 256, 0, ctx().stream>>>(
+      x, R, C, (__half*)hf, (__half*)l16, ld, (f16::Meta*)meta, relu_mode, vec_in);
+  TNN_POST_LAUNCH();
+  prof_end(3);
+  return 0;
+}
+
+int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, int64_t lda,
+                   const void* a_meta, const void* b_hf, const void* b_l16, int64_t ldb,
+                   const void* b_meta, int64_t M, int64_t N, int64_t K, const float* bias, int flags,
+                   int layout, float* act_out, const float* mask_src, void* stat_meta) {
+  TNN_REQUIRE_INIT();
+  if (M <= 0 || N <= 0) return 0;
+  if (K <= 0) TNN_FAIL("tnn_gemm_f16x3: K must be positive");
+  if (M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) TNN_FAIL("tnn_gemm_f16x3: extent above int32");
+  if (!a_meta || !b_meta) TNN_FAIL("tnn_gemm_f16x3: operand meta records are required");
+  if (mask_src && !act_out) TNN_FAIL("tnn_gemm_f16x3: the mask_src form needs act_out");
+  if (act_out && (flags & 2)) TNN_FAIL("tnn_gemm_f16x3: act_out and the relu-in-place flag are exclusive");
+  if (f16::get_encode_fn()) return 1;
+  if (getenv("TNN_EXP_FLAGS")) flags |= atoi(getenv("TNN_EXP_FLAGS")) & (128 | 256);
+  const f16::Meta* ma = (const f16::Meta*)a_meta;
+  const f16::Meta* mb = (const f16::Meta*)b_meta;
+  f16::Meta* st = (f16::Meta*)stat_meta;
+  switch (layout & 3) {
+    case 0: return f16::launch<false, false>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    case 1: return f16::launch<true, false>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    case 2: return f16::launch<false, true>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    default: return f16::launch<true, true>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+  }
+}
+
+}  // extern "C"
