@@ -803,6 +803,9 @@ def split_planes_mix(x):
     return cache["m"]
 
 
+F16_PITCH_PAD = int(os.environ.get("TNN_F16_PITCH_PAD", "0"))   # extra plane pitch, multiple of 8 elements
+
+
 def _new_meta():
     """32-byte operand record of the f16 split (gemm_f16.cu: Meta)"""
     return empty((8,), F32)
@@ -819,7 +822,7 @@ def split_planes_f16(x):
     if "f" in cache:
         return cache["f"]
     R, C = x.shape
-    ld = _round8(C)
+    ld = _round8(C) + F16_PITCH_PAD
     if type(x) is LazyReLU and x._real is None:
         src, relu_mode = x._src, 1
     else:

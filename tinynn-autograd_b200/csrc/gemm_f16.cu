@@ -43,15 +43,21 @@ namespace f16 {
 
 using namespace tnn::tc;
 
-constexpr int BK = 64;                       // 16-bit elements per K block = 128-byte rows
+#ifndef TNN_F16_BK
+#define TNN_F16_BK 64
+#endif
+#ifndef TNN_F16_STAGES
+#define TNN_F16_STAGES (192 / TNN_F16_BK)
+#endif
+constexpr int BK = TNN_F16_BK;               // 16-bit elements per K block: 64 (128-byte rows) or 32
 constexpr int ROWS = 128;                    // rows of A and rows of B staged per CTA
 constexpr int UMMA_N = 256;
 constexpr int TILE_M = 256;                  // CTA pair
 constexpr int UMMA_K = 16;
 constexpr int PLANE_BYTES = ROWS * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = 4 * PLANE_BYTES; // A.hf, A.l, B.hf, B.l
-constexpr int STAGES = 3;
-constexpr int CHUNK_KB = 4;                  // 256 k per TMEM accumulator chunk (as gemm_tc.cu)
+constexpr int STAGES = TNN_F16_STAGES;
+constexpr int CHUNK_KB = 256 / BK;           // 256 k per TMEM accumulator chunk (as gemm_tc.cu)
 constexpr int NUM_THREADS = 384;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int EPI_PATCH_BYTES = 8 * 4096;
@@ -97,9 +103,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)(MN ? (MN_BOX_BYTES >> 4) : 1) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  // K-major rows are BK*2 bytes: 128 B -> SWIZZLE_128B, 8-row groups 1024 B apart; 64 B (BK = 32) ->
+  // SWIZZLE_64B, groups 512 B apart.  MN-major k-rows are always 128 B (64 elements).
+  d |= (uint64_t)(((MN || BK == 64) ? 1024 : 512) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)((MN || BK == 64) ? 2 : 4) << 61;
   return d;
 }
 // D = F32; a_fmt / b_fmt: 0 = F16, 1 = BF16
@@ -111,6 +119,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int b_fmt, bool a_m
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
   tm = t / tiles_n;
   tn = t - tm * tiles_n;
+}
+
+// registers -> swizzled patch for the 32-column block CB of a thread's 128 sums: scale, bias
+template <int CB>
+__device__ __forceinline__ void patch_write(const float (&sum)[128], float4* patch, int lane, float f1,
+                                            float f2, const float* bias_u, int colb, int N) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float4 v = make_float4(sum[CB * 32 + c4 * 4] * f1 * f2, sum[CB * 32 + c4 * 4 + 1] * f1 * f2,
+                           sum[CB * 32 + c4 * 4 + 2] * f1 * f2, sum[CB * 32 + c4 * 4 + 3] * f1 * f2);
+    if (bias_u) {
+      const int c = colb + c4 * 4;
+      if (c + 3 < N) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_u + c);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      } else {
+        if (c < N) v.x += bias_u[c];
+        if (c + 1 < N) v.y += bias_u[c + 1];
+        if (c + 2 < N) v.z += bias_u[c + 2];
+      }
+    }
+    patch[lane * 8 + (c4 ^ (lane & 7))] = v;
+  }
 }
 
 // flags: 1 accumulate into D, 2 ReLU in place, 8 statistics of relu(D) instead of D
@@ -252,16 +283,31 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+#ifdef TNN_F16_PROBE
+      long long w_full = 0, w_empty = 0, t_begin = clock64();
+#endif
       for (int u = group; u < num_units; u += num_groups) {
         int t, sp, kb_begin, kb_end;
         decode(u, t, sp, kb_begin, kb_end);
         for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
+#ifdef TNN_F16_PROBE
+          long long p0 = clock64();
+#endif
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+#ifdef TNN_F16_PROBE
+          w_empty += clock64() - p0;
+#endif
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * UMMA_N);
           const int kb1 = min(kb0 + CHUNK_KB, kb_end);
           for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef TNN_F16_PROBE
+            long long p1 = clock64();
+#endif
             mbar_wait(full_bar(stage), phase);
+#ifdef TNN_F16_PROBE
+            w_full += clock64() - p1;
+#endif
             tc_fence_after();
             const uint32_t sa_h = smem_base + stage * STAGE_BYTES;
             const uint32_t sa_l = sa_h + PLANE_BYTES;
@@ -294,6 +340,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
           }
         }
       }
+#ifdef TNN_F16_PROBE
+      if (group == 0 || group == 37)
+        printf("probe group %d: loop %lld cycles, wait full %lld, wait tmem-empty %lld\n", group,
+               clock64() - t_begin, w_full, w_empty);
+#endif
     }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -339,7 +390,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -362,102 +413,118 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         __threadfence();
       }
       {
+        // ---- store the tile.  Each warp bounces its 32 x 32 blocks through a private 4 KB swizzled
+        // shared-memory patch and comes back with 8 lanes per row, so every global access is 4 full
+        // 128-byte lines.  The MMA issuer can only run two chunks ahead while the epilogue warps are
+        // here, so this phase is on the critical path: the code is kept SMALL (one rolled copy of
+        // the store loop; a fully unrolled version was 8,000 SASS instructions that every warp
+        // walked once per tile, instruction-fetch-bound at ~40 k cycles per tile).
         const int row_base = tm * TILE_M + (int)cta_rank * ROWS + quad * 32;
         float4* patch = reinterpret_cast<float4*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
         const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
         const bool act_aligned = !emit_act || (((reinterpret_cast<uintptr_t>(act_out) |
                                                   reinterpret_cast<uintptr_t>(mask_src)) & 15) == 0);
-        const bool fast_rows = rows_aligned && act_aligned;
         const bool want_mask = emit_act && mask_src != nullptr;
-#pragma unroll
+        const bool want_relu_side = !want_mask && (emit_act || (flags & 8));
+        const float* pre_src = accumulate ? D : (want_mask ? mask_src : nullptr);
+        const int rr = lane >> 3, c4l = lane & 7;
+#pragma unroll 1
         for (int cb = 0; cb < 4; ++cb) {
           const int colb = col0 + cb * 32;
-          if (colb >= N) break;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float4 v = make_float4(sum[cb * 32 + c4 * 4] * f1 * f2, sum[cb * 32 + c4 * 4 + 1] * f1 * f2,
-                                   sum[cb * 32 + c4 * 4 + 2] * f1 * f2, sum[cb * 32 + c4 * 4 + 3] * f1 * f2);
-            if (bias_u) {
-              const int c = colb + c4 * 4;
-              if (c + 3 < N) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_u + c);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              } else {
-                if (c < N) v.x += bias_u[c];
-                if (c + 1 < N) v.y += bias_u[c + 1];
-                if (c + 2 < N) v.z += bias_u[c + 2];
-              }
-            }
-            patch[lane * 8 + (c4 ^ (lane & 7))] = v;
+          if (colb >= N) break;                                 // warp-uniform
+          switch (cb) {                                         // register indices are compile-time
+            case 0: patch_write<0>(sum, patch, lane, f1, f2, bias_u, colb, N); break;
+            case 1: patch_write<1>(sum, patch, lane, f1, f2, bias_u, colb, N); break;
+            case 2: patch_write<2>(sum, patch, lane, f1, f2, bias_u, colb, N); break;
+            default: patch_write<3>(sum, patch, lane, f1, f2, bias_u, colb, N); break;
           }
           __syncwarp();
-          const float* pre_src = accumulate ? D : (want_mask ? mask_src : nullptr);
-          float4 pre[8];
-          if (fast_rows && pre_src != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int grow = row_base + 4 * i + (lane >> 3), gcol = colb + (lane & 7) * 4;
-              if (grow < M && gcol + 3 < N)
-                pre[i] = *reinterpret_cast<const float4*>(pre_src + (int64_t)grow * ldd + gcol);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3), c4 = lane & 7;
-            float4 v = patch[r * 8 + (c4 ^ (r & 7))];
-            const int grow = row_base + r, gcol = colb + c4 * 4;
-            if (grow < M && gcol < N) {
-              float* dp = D + (int64_t)grow * ldd + gcol;
-              float e[4];
-              const int nvalid = min(4, N - gcol);
-              if (nvalid == 4 && fast_rows) {
-                if (accumulate) {
-                  const float4 o = pre[i];
-                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                }
+          const int gcol = colb + c4l * 4;
+          if (rows_aligned && act_aligned && colb + 32 <= N) {
+            if (pre_src == nullptr) {
+              // plain / relu / statistics: nothing to read back
+#pragma unroll 1
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + rr, grow = row_base + r;
+                if (grow >= M) break;
+                float4 v = patch[r * 8 + (c4l ^ (r & 7))];
                 if (relu) {
                   v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
                   v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 }
-                *reinterpret_cast<float4*>(dp) = v;
-                e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
-                if (want_mask) {
-                  // act = D * (pre-activation >= 0): the ReLU gradient mask of ops.py:336-343
-                  const float4 z = accumulate
-                      ? *reinterpret_cast<const float4*>(mask_src + (int64_t)grow * ldd + gcol)
-                      : pre[i];
-                  e[0] = z.x >= 0.f ? v.x : v.x * 0.f; e[1] = z.y >= 0.f ? v.y : v.y * 0.f;
-                  e[2] = z.z >= 0.f ? v.z : v.z * 0.f; e[3] = z.w >= 0.f ? v.w : v.w * 0.f;
-                } else if (emit_act || (flags & 8)) {
-                  // ReLU(D), NaN-propagating like np.clip
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) e[k] = e[k] < 0.f ? 0.f : e[k];
+                *reinterpret_cast<float4*>(D + (int64_t)grow * ldd + gcol) = v;
+                if (want_relu_side) {                          // ReLU(D), NaN-propagating like np.clip
+                  v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+                  v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+                  if (emit_act) *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = v;
                 }
-                if (emit_act)
-                  *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = make_float4(e[0], e[1], e[2], e[3]);
-              } else {
-                const float s[4] = {v.x, v.y, v.z, v.w};
+                if (want_stats)
+                  st_max = max(max(st_max, __float_as_uint(v.x) & 0x7FFFFFFFu),
+                               max(max(__float_as_uint(v.y) & 0x7FFFFFFFu, __float_as_uint(v.z) & 0x7FFFFFFFu),
+                                   __float_as_uint(v.w) & 0x7FFFFFFFu));
+              }
+            } else {
+              // accumulate-into-D and / or the ReLU-backward mask: whatever has to be READ first is
+              // fetched for all 8 row groups up front (8 independent 128-bit loads in flight)
+              float4 pre[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  e[k] = 0.f;
-                  if (k < nvalid) {
-                    float x = s[k];
-                    if (accumulate) x += dp[k];
-                    if (relu) x = fmaxf(x, 0.f);
-                    dp[k] = x;
-                    float a = x;
-                    if (want_mask) a = mask_src[(int64_t)grow * ldd + gcol + k] >= 0.f ? x : x * 0.f;
-                    else if (emit_act || (flags & 8)) a = x < 0.f ? 0.f : x;
-                    if (emit_act) act_out[(int64_t)grow * ldd + gcol + k] = a;
-                    e[k] = a;
+              for (int i = 0; i < 8; ++i) {
+                const int grow = row_base + 4 * i + rr;
+                if (grow < M) pre[i] = *reinterpret_cast<const float4*>(pre_src + (int64_t)grow * ldd + gcol);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + rr, grow = row_base + r;
+                if (grow < M) {
+                  float4 v = patch[r * 8 + (c4l ^ (r & 7))];
+                  if (accumulate) {
+                    v.x += pre[i].x; v.y += pre[i].y; v.z += pre[i].z; v.w += pre[i].w;
                   }
+                  if (relu) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                    v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                  }
+                  *reinterpret_cast<float4*>(D + (int64_t)grow * ldd + gcol) = v;
+                  if (want_mask) {
+                    // act = D * (pre-activation >= 0): the ReLU gradient mask of ops.py:336-343
+                    const float4 z = accumulate
+                        ? *reinterpret_cast<const float4*>(mask_src + (int64_t)grow * ldd + gcol)
+                        : pre[i];
+                    v.x = z.x >= 0.f ? v.x : v.x * 0.f; v.y = z.y >= 0.f ? v.y : v.y * 0.f;
+                    v.z = z.z >= 0.f ? v.z : v.z * 0.f; v.w = z.w >= 0.f ? v.w : v.w * 0.f;
+                  } else if (want_relu_side) {
+                    v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+                    v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+                  }
+                  if (emit_act) *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = v;
+                  if (want_stats)
+                    st_max = max(max(st_max, __float_as_uint(v.x) & 0x7FFFFFFFu),
+                                 max(max(__float_as_uint(v.y) & 0x7FFFFFFFu, __float_as_uint(v.z) & 0x7FFFFFFFu),
+                                     __float_as_uint(v.w) & 0x7FFFFFFFu));
                 }
               }
-              if (want_stats) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  st_max = max(st_max, __float_as_uint(e[k]) & 0x7FFFFFFFu);
-                }
+            }
+          } else {
+            // ragged right edge or unaligned rows: element by element
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + rr, grow = row_base + r;
+              if (grow >= M) break;
+              const float4 v4 = patch[r * 8 + (c4l ^ (r & 7))];
+              const float s[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll 1
+              for (int k = 0; k < 4; ++k) {
+                if (gcol + k >= N) break;
+                const int64_t off = (int64_t)grow * ldd + gcol + k;
+                float x = k == 0 ? s[0] : (k == 1 ? s[1] : (k == 2 ? s[2] : s[3]));
+                if (accumulate) x += D[off];
+                if (relu) x = fmaxf(x, 0.f);
+                D[off] = x;
+                float a = x;
+                if (want_mask) a = mask_src[off] >= 0.f ? x : x * 0.f;
+                else if (want_relu_side) a = x < 0.f ? 0.f : x;
+                if (emit_act) act_out[off] = a;
+                if (want_stats) st_max = max(st_max, __float_as_uint(a) & 0x7FFFFFFFu);
               }
             }
           }
@@ -608,11 +675,12 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
   if (ld % 8 != 0) TNN_FAIL("f16 GEMM: operand pitch must be a multiple of 8 elements");
   cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)(mn_major ? BK : ROWS)};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 64 : BK), (cuuint32_t)(mn_major ? BK : ROWS)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        (mn_major || BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) TNN_FAIL("cuTensorMapEncodeTiled (f16 planes) failed with code " + std::to_string((int)r));
   return 0;
@@ -645,7 +713,7 @@ static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64
     const int64_t rem = tiles % max_groups;
     if (rem > 0) {
       int s = 1;
-      while (s < 4 && rem * (s * 2) <= max_groups && num_kb / (s * 2) >= 8) s *= 2;
+      while (s < 4 && rem * (s * 2) <= max_groups && num_kb / (s * 2) >= 512 / BK) s *= 2;
       if (s > 1) {
         t_full = (int)(tiles - rem);
         tail_split = s;

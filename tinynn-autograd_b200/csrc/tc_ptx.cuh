@@ -50,6 +50,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
          (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
 }
+// same, without release semantics: for signals that publish no memory writes (an epilogue warp
+// handing a TMEM accumulator back after tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The
+// release form compiles to MEMBAR.ALL.CTA + ERRBAR, which waits for every outstanding global store of
+// the warp -- i.e. for the whole tile just written.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
