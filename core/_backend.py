@@ -108,8 +108,9 @@ _SIGNATURES = {
     "tnn_split_f16": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_gemm_f16x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64,
                        _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
-    "tnn_split_tf32_bf16_cond": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_int,
-                                 _c_vp],
+    "tnn_split_tf32_bf16_cond": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_int,
+                                 _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_vp],
+    "tnn_f16_stats_cond": [_c_vp, _c_i64, _c_vp, _c_int],
     "tnn_gemm_tf32_bf16x2_cond": [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64,
                                   _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "tnn_set_gemm_cta_group": [_c_int],
@@ -832,6 +833,10 @@ def split_planes_f16(x):
         meta = _new_meta()
         if _lib.tnn_f16_stats(src.ptr, R * C, meta.ptr, relu_mode):
             _raise("tnn_f16_stats")
+    elif _lib.tnn_f16_stats_cond(src.ptr, R * C, meta.ptr, relu_mode):
+        # (the producer's epilogue normally recorded them; this launch only works when the producer
+        # was the fallback product, which records none)
+        _raise("tnn_f16_stats_cond")
     hf, l16 = _empty_bf16(R, ld), _empty_bf16(R, ld)
     if _lib.tnn_split_f16(src.ptr, R, C, hf.ptr, l16.ptr, ld, meta.ptr, relu_mode):
         _raise("tnn_split_f16")
@@ -885,11 +890,9 @@ def _matmul_f16(a, b, ta, tb, bias, out, flags, act, mask_src, M, N, K):
     fa = _fallback_planes(0, a.shape[0], lda)
     fb = _fallback_planes(1, b.shape[0], ldb)
     if _lib.tnn_split_tf32_bf16_cond(a_src.ptr, a.shape[0], a.shape[1], fa[0].ptr, fa[1].ptr, fa[2].ptr, lda,
-                                     a_meta.ptr, b_meta.ptr, a_relu,
+                                     a_relu, b_src.ptr, b.shape[0], b.shape[1], fb[0].ptr, fb[1].ptr,
+                                     fb[2].ptr, ldb, b_relu, a_meta.ptr, b_meta.ptr,
                                      stat.ptr if stat is not None else None):
-        _raise("tnn_split_tf32_bf16_cond")
-    if _lib.tnn_split_tf32_bf16_cond(b_src.ptr, b.shape[0], b.shape[1], fb[0].ptr, fb[1].ptr, fb[2].ptr, ldb,
-                                     a_meta.ptr, b_meta.ptr, b_relu, None):
         _raise("tnn_split_tf32_bf16_cond")
     if _lib.tnn_gemm_tf32_bf16x2_cond(out.ptr, N, fa[0].ptr, fa[1].ptr, fa[2].ptr, lda, fb[0].ptr, fb[1].ptr,
                                       fb[2].ptr, ldb, M, N, K, bias_p, flags & 3, layout,

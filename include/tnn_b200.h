@@ -259,8 +259,10 @@ int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
  * tnn_split_tf32_bf16_cond / tnn_gemm_tf32_bf16x2_cond: the fallback for operands outside the guard,
  *   launched unconditionally behind tnn_gemm_f16x3: they return at once when both records say safe,
  *   otherwise split (relu_mode: relu(x)) / multiply with the mixed split above.  No host round trip.
- *   poison_meta (optional): the record tnn_gemm_f16x3 would have filled with its result's statistics;
- *   the fallback marks it non-finite, so the next f16 split of that result falls back as well. */
+ *   The split takes both operands in one launch.  result_meta (optional): the record tnn_gemm_f16x3
+ *   would have filled with its result's statistics; the fallback marks it "statistics missing" and
+ * tnn_f16_stats_cond, launched before the next split of that result, then computes them (it returns
+ *   at once otherwise). */
 int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode);
 int tnn_f16_meta_reset(void* meta);
 int tnn_split_f16(const float* x, int64_t R, int64_t C, void* hf, void* l16, int64_t ld, void* meta,
@@ -269,9 +271,11 @@ int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, i
                    const void* a_meta, const void* b_hf, const void* b_l16, int64_t ldb,
                    const void* b_meta, int64_t M, int64_t N, int64_t K, const float* bias, int flags,
                    int layout, float* act_out, const float* mask_src, void* stat_meta);
-int tnn_split_tf32_bf16_cond(const float* x, int64_t R, int64_t C, float* hi, void* h16, void* l16,
-                             int64_t ld, const void* meta_a, const void* meta_b, int relu_mode,
-                             void* poison_meta);
+int tnn_split_tf32_bf16_cond(const float* xa, int64_t Ra, int64_t Ca, float* hia, void* h16a, void* l16a,
+                             int64_t lda, int relu_a, const float* xb, int64_t Rb, int64_t Cb, float* hib,
+                             void* h16b, void* l16b, int64_t ldb, int relu_b, const void* meta_a,
+                             const void* meta_b, void* result_meta);
+int tnn_f16_stats_cond(const float* x, int64_t n, void* meta, int relu_mode);
 int tnn_gemm_tf32_bf16x2_cond(float* D, int64_t ldd, const float* a_hi, const void* a_h16,
                               const void* a_l16, int64_t lda, const float* b_hi, const void* b_h16,
                               const void* b_l16, int64_t ldb, int64_t M, int64_t N, int64_t K,

@@ -62,6 +62,12 @@ def main():
     ref = a.astype(np.float64) @ b.astype(np.float64)
     denom = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
     print("fallback rows*1e-30: max err/(|A||B|) = %.2e" % float(np.max(np.abs(out - ref) / denom)))
+    # fallback product with a fused relu output feeding the next product (statistics recomputed on demand)
+    z, act = be.matmul(be.from_numpy(a), be.from_numpy(b), act=True)
+    w2 = rng.standard_normal((N, 256)).astype(np.float32)
+    nxt = be.matmul(act, be.from_numpy(w2)).numpy().astype(np.float64)
+    ref2 = np.maximum(ref, 0) @ w2.astype(np.float64)
+    print("fallback -> relu -> next product: rel err %.2e" % rel(nxt, ref2))
     a[3, 5] = np.inf
     out = be.matmul(be.from_numpy(a), be.from_numpy(b)).numpy()
     print("inf row non-finite:", bool(np.all(~np.isfinite(out[3]))), " other rows finite:",

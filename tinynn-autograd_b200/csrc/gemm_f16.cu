@@ -70,7 +70,7 @@ constexpr unsigned int GUARD_FRACTION = 256; // unsafe when small non-zeros * 25
 // the rest by split_f16_kernel.  Word 3 (`safe`) is what the conditional kernels of gemm_tc.cu read.
 struct Meta {
   unsigned int absmax;      // bits of max |x| (NaN sorts above Inf)
-  unsigned int reserved;
+  unsigned int need_stats;  // set by the fallback product: absmax of its result was not recorded
   int exp;                  // planes hold x * 2^exp
   int safe;                 // 1: planes are valid and inside the guard
   unsigned int n_small;     // non-zero elements with |X| < SMALL_LIMIT
@@ -116,9 +116,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int b_fmt, bool a_m
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(UMMA_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
-  tm = t / tiles_n;
-  tn = t - tm * tiles_n;
+// group_m = 1: row-major.  group_m = -g: column panels of g tile columns (all tile rows of a panel,
+// row-major inside it, before the next panel), so the panel's B operand stays L2-resident.
+// group_m = g > 1: row groups (consecutive tiles walk g tile rows before the next tile column).
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  if (group_m == 1) {
+    tm = t / tiles_n;
+    tn = t - tm * tiles_n;
+  } else if (group_m < 0) {
+    const int gn = -group_m;
+    const int per_panel = tiles_m * gn;
+    const int g = t / per_panel;
+    const int first_n = g * gn;
+    const int cols = min(gn, tiles_n - first_n);
+    const int r = t - g * per_panel;
+    tm = r / cols;
+    tn = first_n + r % cols;
+  } else {
+    const int per_group = group_m * tiles_n;
+    const int g = t / per_group;
+    const int first_m = g * group_m;
+    const int rows = min(group_m, tiles_m - first_m);
+    const int r = t - g * per_group;
+    tm = first_m + r % rows;
+    tn = r / rows;
+  }
 }
 
 // registers -> swizzled patch for the 32-column block CB of a thread's 128 sums: scale, bias
@@ -153,7 +175,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
                   const float* __restrict__ bias, int flags, int t_full, int tail_split,
                   unsigned int* __restrict__ tile_flags, float* __restrict__ act_out,
                   const float* __restrict__ mask_src, const Meta* __restrict__ meta_a,
-                  const Meta* __restrict__ meta_b, Meta* __restrict__ stat_out) {
+                  const Meta* __restrict__ meta_b, Meta* __restrict__ stat_out, int group_m) {
   // operands outside the guard: the conditional mixed-split launches behind this one take over
   if (!(meta_a->safe && meta_b->safe)) return;
   extern __shared__ uint8_t smem_raw[];
@@ -229,7 +251,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         int t, sp, kb_begin, kb_end;
         decode(u, t, sp, kb_begin, kb_end);
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_n, tm, tn);
+        tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
         const int row_a = tm * TILE_M + (int)cta_rank * ROWS;
         const int row_b = tn * UMMA_N + (int)cta_rank * ROWS;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -370,7 +392,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
       const bool want_stats = stat_out != nullptr && final_unit;
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_n, tm, tn);
+      tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
       const int col0 = tn * UMMA_N + half * 128;
       float sum[128];
 #pragma unroll
@@ -557,7 +579,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
 
 // max |x| of (relu_mode ? relu(x) : x) over n elements -> meta->absmax (integer atomicMax)
 __global__ void __launch_bounds__(256)
-stats_kernel(const float* __restrict__ x, int64_t n, Meta* __restrict__ meta, int relu_mode, int vec) {
+stats_kernel(const float* __restrict__ x, int64_t n, Meta* __restrict__ meta, int relu_mode, int vec,
+             int only_if_needed) {
+  if (only_if_needed && !meta->need_stats) return;
   unsigned int mx = 0u;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   auto take = [&](float v) {
@@ -689,6 +713,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
 static unsigned int* g_tile_flags = nullptr;
 constexpr int MAX_FLAG_TILES = 1 << 16;
 static bool g_attr_set[2][2] = {};
+static int g_group_m = -8;     // tile rasterisation: panels of 8 tile columns measured 1-2 % ahead of row-major; (TNN_F16_GROUP_M), see tile_coords
 
 template <bool A_MN, bool B_MN>
 static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64_t lda, const void* b_h,
@@ -740,7 +765,7 @@ static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64
   cfg.numAttrs = 1;
   prof_begin(1);
   TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_h, ma_l, mb_h, mb_l, D, ldd, (int)M, (int)N, (int)K, bias, flags,
-                              t_full, tail_split, g_tile_flags, act_out, mask_src, meta_a, meta_b, stat_out));
+                              t_full, tail_split, g_tile_flags, act_out, mask_src, meta_a, meta_b, stat_out, g_group_m));
   ctx().launches++;
   prof_end(1);
   return 0;
@@ -760,7 +785,19 @@ int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode) {
   if (n <= 0) return 0;
   const int vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   prof_begin(3);
-  f16::stats_kernel<<<ew_grid(ceil_div(n, 16), 256), 256, 0, ctx().stream>>>(x, n, (f16::Meta*)meta, relu_mode, vec);
+  f16::stats_kernel<<<ew_grid(ceil_div(n, 16), 256), 256, 0, ctx().stream>>>(x, n, (f16::Meta*)meta, relu_mode, vec, 0);
+  TNN_POST_LAUNCH();
+  prof_end(3);
+  return 0;
+}
+
+int tnn_f16_stats_cond(const float* x, int64_t n, void* meta, int relu_mode) {
+  TNN_REQUIRE_INIT();
+  if (!meta) TNN_FAIL("tnn_f16_stats_cond: meta is required");
+  if (n <= 0) return 0;
+  const int vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  prof_begin(3);
+  f16::stats_kernel<<<ew_grid(ceil_div(n, 16), 256, 4), 256, 0, ctx().stream>>>(x, n, (f16::Meta*)meta, relu_mode, vec, 1);
   TNN_POST_LAUNCH();
   prof_end(3);
   return 0;
@@ -801,6 +838,12 @@ int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, i
   if (act_out && (flags & 2)) TNN_FAIL("tnn_gemm_f16x3: act_out and the relu-in-place flag are exclusive");
   if (f16::get_encode_fn()) return 1;
   if (getenv("TNN_EXP_FLAGS")) flags |= atoi(getenv("TNN_EXP_FLAGS")) & (128 | 256);
+  static bool env_read = false;
+  if (!env_read) {
+    const char* gm = getenv("TNN_F16_GROUP_M");
+    if (gm && atoi(gm) != 0 && atoi(gm) >= -64 && atoi(gm) <= 64) f16::g_group_m = atoi(gm);
+    env_read = true;
+  }
   const f16::Meta* ma = (const f16::Meta*)a_meta;
   const f16::Meta* mb = (const f16::Meta*)b_meta;
   f16::Meta* st = (f16::Meta*)stat_meta;

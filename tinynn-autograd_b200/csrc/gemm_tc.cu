@@ -733,15 +733,10 @@ split_tf32_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __re
 // fp32 [R, C] -> hi = tf32(x) (fp32 plane), h16 = bf16(x), l16 = bf16(x - hi), all with pitch ld
 // (a multiple of 8 >= C; the pad columns receive zeros).  One thread per 8 consecutive columns:
 // two 128-bit loads, two 128-bit hi stores, one 128-bit store per bf16 plane.  12 B/element.
-__global__ void __launch_bounds__(256)
-split_mix_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __restrict__ hi,
-                 __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ l16, int64_t ld,
-                 int vec_in, const int* __restrict__ cond_a, const int* __restrict__ cond_b,
-                 int relu_mode, unsigned int* __restrict__ poison) {
-  if (cond_a != nullptr && cond_a[3] && cond_b[3]) return;   // see gemm_tf32x3_kernel
-  // the fallback product leaves no statistics of its result: mark that record non-finite so the
-  // next f16 split of the result falls back too instead of trusting an empty record
-  if (poison != nullptr && blockIdx.x == 0 && threadIdx.x == 0) poison[0] = 0x7FFFFFFFu;
+__device__ __forceinline__ void split_mix_body(const float* __restrict__ x, int64_t R, int64_t C,
+                                               float* __restrict__ hi, __nv_bfloat16* __restrict__ h16,
+                                               __nv_bfloat16* __restrict__ l16, int64_t ld, int vec_in,
+                                               int relu_mode) {
   const int64_t gpr = ld / 8;   // 8-column groups per row
   const int64_t total = R * gpr;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -776,6 +771,31 @@ split_mix_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __res
     *reinterpret_cast<uint4*>(h16 + r * ld + c) = ph.u;
     *reinterpret_cast<uint4*>(l16 + r * ld + c) = pl.u;
   }
+}
+
+__global__ void __launch_bounds__(256)
+split_mix_kernel(const float* __restrict__ x, int64_t R, int64_t C, float* __restrict__ hi,
+                 __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ l16, int64_t ld,
+                 int vec_in) {
+  split_mix_body(x, R, C, hi, h16, l16, ld, vec_in, 0);
+}
+
+// Conditional form, both operands of a product in one launch (blockIdx.y picks the operand): the
+// fallback behind an f16 product (gemm_f16.cu).  Returns at once when both operands were inside
+// the f16 guard (word 3 of an operand's meta record = its `safe` flag).  When it does run, the
+// mixed-split product that follows leaves no statistics of its result, so word 1 of the result's
+// record ("statistics missing") is set and tnn_f16_stats_cond recomputes them for the next split.
+struct SplitArgs {
+  const float* x; int64_t R, C; float* hi; __nv_bfloat16* h16; __nv_bfloat16* l16; int64_t ld;
+  int vec_in, relu_mode;
+};
+__global__ void __launch_bounds__(256)
+split_mix_cond2_kernel(SplitArgs a, SplitArgs b, const int* __restrict__ cond_a,
+                       const int* __restrict__ cond_b, unsigned int* __restrict__ result_meta) {
+  if (cond_a[3] && cond_b[3]) return;
+  if (result_meta != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) result_meta[1] = 1u;
+  const SplitArgs& s = blockIdx.y == 0 ? a : b;
+  split_mix_body(s.x, s.R, s.C, s.hi, s.h16, s.l16, s.ld, s.vec_in, s.relu_mode);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -1065,25 +1085,31 @@ int tnn_split_tf32_bf16(const float* x, int64_t R, int64_t C, float* hi, void* h
   const int vec_in = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   prof_begin(3);
   tc::split_mix_kernel<<<ew_grid(R * (ld / 8), 256), 256, 0, ctx().stream>>>(
-      x, R, C, hi, (__nv_bfloat16*)h16, (__nv_bfloat16*)l16, ld, vec_in, nullptr, nullptr, 0, nullptr);
+      x, R, C, hi, (__nv_bfloat16*)h16, (__nv_bfloat16*)l16, ld, vec_in);
   TNN_POST_LAUNCH();
   prof_end(3);
   return 0;
 }
 
-int tnn_split_tf32_bf16_cond(const float* x, int64_t R, int64_t C, float* hi, void* h16, void* l16,
-                             int64_t ld, const void* meta_a, const void* meta_b, int relu_mode,
-                             void* poison_meta) {
+int tnn_split_tf32_bf16_cond(const float* xa, int64_t Ra, int64_t Ca, float* hia, void* h16a, void* l16a,
+                             int64_t lda, int relu_a, const float* xb, int64_t Rb, int64_t Cb, float* hib,
+                             void* h16b, void* l16b, int64_t ldb, int relu_b, const void* meta_a,
+                             const void* meta_b, void* result_meta) {
   TNN_REQUIRE_INIT();
-  if (R <= 0 || C <= 0) return 0;
-  if (!hi || !h16 || !l16) TNN_FAIL("tnn_split_tf32_bf16_cond: all three planes are required");
-  if ((meta_a == nullptr) != (meta_b == nullptr)) TNN_FAIL("tnn_split_tf32_bf16_cond: meta records come in pairs");
-  if (ld % 8 != 0 || ld < C) TNN_FAIL("tnn_split_tf32_bf16_cond: ld must be >= C and a multiple of 8");
-  const int vec_in = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (Ra <= 0 || Ca <= 0 || Rb <= 0 || Cb <= 0) return 0;
+  if (!hia || !h16a || !l16a || !hib || !h16b || !l16b) TNN_FAIL("tnn_split_tf32_bf16_cond: all planes are required");
+  if (!meta_a || !meta_b) TNN_FAIL("tnn_split_tf32_bf16_cond: both operand meta records are required");
+  if (lda % 8 != 0 || lda < Ca || ldb % 8 != 0 || ldb < Cb)
+    TNN_FAIL("tnn_split_tf32_bf16_cond: pitches must be >= C and multiples of 8");
+  tc::SplitArgs a{xa, Ra, Ca, hia, (__nv_bfloat16*)h16a, (__nv_bfloat16*)l16a, lda,
+                  (Ca % 4 == 0) && ((reinterpret_cast<uintptr_t>(xa) & 15) == 0), relu_a};
+  tc::SplitArgs b{xb, Rb, Cb, hib, (__nv_bfloat16*)h16b, (__nv_bfloat16*)l16b, ldb,
+                  (Cb % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0), relu_b};
+  // a small grid: this launch returns at once in all but exceptional steps
+  dim3 grid((unsigned)ew_grid(std::max(Ra * (lda / 8), Rb * (ldb / 8)), 256, 4), 2);
   prof_begin(3);
-  tc::split_mix_kernel<<<ew_grid(R * (ld / 8), 256), 256, 0, ctx().stream>>>(
-      x, R, C, hi, (__nv_bfloat16*)h16, (__nv_bfloat16*)l16, ld, vec_in, (const int*)meta_a,
-      (const int*)meta_b, relu_mode, (unsigned int*)poison_meta);
+  tc::split_mix_cond2_kernel<<<grid, 256, 0, ctx().stream>>>(a, b, (const int*)meta_a, (const int*)meta_b,
+                                                             (unsigned int*)result_meta);
   TNN_POST_LAUNCH();
   prof_end(3);
   return 0;
