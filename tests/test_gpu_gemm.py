@@ -154,6 +154,176 @@ def test_fused_activation_outputs(be, split):
         be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
 
 
+def _meta(rec):
+    w = rec.numpy().view(np.uint32)
+    return dict(absmax=w[0:1].view(np.float32)[0], need_stats=int(w[1]), exp=int(w[2:3].view(np.int32)[0]),
+                safe=int(w[3]), n_small=int(w[4]), n_nz=int(w[5]))
+
+
+def test_f16_split_planes(be):
+    """scaled fp16 hi/lo planes (gemm_f16.cu): bit-identical to the numpy model of
+    oracle/split_error_model.py, pad columns zero, record = (absmax, exponent, counts, safe)"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import split_error_model as S
+    rng = np.random.RandomState(0)
+    for R_, C_, scale in ((64, 64, 1.0), (130, 70, 3e-4), (257, 33, 7e5), (5, 1000, 1e-12), (3, 1, 2.0)):
+        x = (rng.standard_normal((R_, C_)) * scale * np.exp2(rng.randint(-12, 1, (R_, C_)))).astype(np.float32)
+        d = be.from_numpy(x)
+        hf, l16, ld, meta, _, relu_mode = be.split_planes_f16(d)
+        assert ld % 8 == 0 and ld >= C_ and relu_mode == 0
+        H = hf.numpy().view(np.float16).reshape(R_, ld)
+        L = l16.numpy().view(np.float16).reshape(R_, ld)
+        m = _meta(meta)
+        rh, rl, e = S.f16_planes(x)
+        assert m["exp"] == e and m["safe"] == 1 and m["absmax"] == np.max(np.abs(x))
+        assert m["n_nz"] == int(np.sum(x != 0))
+        assert np.all(H[:, C_:] == 0) and np.all(L[:, C_:] == 0)
+        assert np.array_equal(H[:, :C_].astype(np.float32), rh)
+        assert np.array_equal(L[:, :C_].astype(np.float32), rl)
+    # relu applied on load (a LazyReLU is split from its pre-activation)
+    z = be.from_numpy(rng.standard_normal((64, 96)).astype(np.float32))
+    lazy = be.LazyReLU(z)
+    hf, l16, ld, meta, src, relu_mode = be.split_planes_f16(lazy)
+    assert relu_mode == 1 and src is z and lazy._real is None
+    rh, rl, e = S.f16_planes(np.maximum(z.numpy(), 0))
+    assert np.array_equal(hf.numpy().view(np.float16).reshape(64, ld)[:, :96].astype(np.float32), rh)
+
+
+@pytest.mark.parametrize("shape", [
+    (128, 256, 64), (256, 256, 128), (256, 512, 96), (384, 768, 200), (100, 300, 52), (129, 257, 36),
+    (1000, 520, 260), (2048, 1024, 512), (64, 64, 32), (300, 72, 4100),
+])
+def test_f16_gemm_shapes(be, shape):
+    """default path: NN / NT / TN (+ accumulate) / relu epilogue on operands of very different
+    magnitudes (the per-tensor scale exponents are exercised), rel 1e-5 of max|ref|"""
+    M, N, K = shape
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "f16"
+    try:
+        rng = np.random.RandomState(M * 7 + N * 3 + K)
+        a = (rng.standard_normal((M, K)) * 3.7e-6).astype(np.float32)
+        b = (rng.standard_normal((K, N)) * 4.1e4).astype(np.float32)
+        bias = rng.standard_normal((1, N)).astype(np.float32)
+        da, db, dbias = be.from_numpy(a), be.from_numpy(b), be.from_numpy(bias)
+        assert be.use_tensor_cores(M, N, K, be.F32)
+        ref = _ref(a, b, False, False, bias)
+        assert op_cases.rel_err(be.matmul(da, db, bias=dbias).numpy(), ref) <= TOL
+        assert _meta(da.split["f"][3])["safe"] == 1 and _meta(db.split["f"][3])["safe"] == 1
+        bt = np.ascontiguousarray(b.T)
+        assert op_cases.rel_err(be.matmul(da, be.from_numpy(bt), tb=True).numpy(), _ref(a, bt, False, True, None)) <= TOL
+        at = np.ascontiguousarray(a.T)
+        c0 = rng.standard_normal((M, N)).astype(np.float32)
+        outs = []
+        for _ in range(2):
+            dc = be.from_numpy(c0)
+            be.matmul(be.from_numpy(at), db, ta=True, out=dc, accumulate=True)
+            outs.append(dc.numpy())
+        assert op_cases.rel_err(outs[0], _ref(at, b, True, False, None) + c0) <= TOL
+        assert np.array_equal(outs[0], outs[1])                       # run-to-run identical
+        out = be.matmul(da, db, bias=dbias, relu=True).numpy()
+        assert op_cases.rel_err(out, np.maximum(ref, 0)) <= TOL
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+
+
+def test_f16_fused_outputs(be):
+    """act=True on the default path: the launch stores the pre-activation and records max|relu(z)| for
+    the next split (the fp32 activation is a LazyReLU, never written); the next product consumes it.
+    mask_src form: second output = out * (mask_src >= 0), with its statistics"""
+    rng = np.random.RandomState(5)
+    M, N, K = 300, 264, 136
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal((1, N)).astype(np.float32)
+    w2 = rng.standard_normal((N, 72)).astype(np.float32)
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "f16"
+    try:
+        z, act = be.matmul(be.from_numpy(a), be.from_numpy(b), bias=be.from_numpy(bias), act=True)
+        assert op_cases.rel_err(z.numpy(), _ref(a, b, False, False, bias)) <= TOL
+        assert type(act) is be.LazyReLU and act._real is None
+        m = _meta(act.split["stat"])
+        assert m["absmax"] == np.max(np.maximum(z.numpy(), 0)) and m["need_stats"] == 0
+        y_fused = be.matmul(act, be.from_numpy(w2)).numpy()
+        assert act._real is None                                   # still never materialised
+        y_plain = be.matmul(be.from_numpy(np.maximum(z.numpy(), 0)), be.from_numpy(w2)).numpy()
+        assert np.array_equal(y_fused, y_plain)
+        assert np.array_equal(act.numpy(), np.maximum(z.numpy(), 0))
+        pre = rng.standard_normal((M, N)).astype(np.float32)
+        g, masked = be.matmul(be.from_numpy(a), be.from_numpy(b), act=True, mask_src=be.from_numpy(pre))
+        assert np.array_equal(masked.numpy(), g.numpy() * (pre >= 0))
+        assert _meta(masked.split["stat"])["absmax"] == np.max(np.abs(masked.numpy()))
+        y1 = be.matmul(masked, be.from_numpy(w2)).numpy()
+        y2 = be.matmul(be.from_numpy(masked.numpy()), be.from_numpy(w2)).numpy()
+        assert np.array_equal(y1, y2)
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+
+
+def test_f16_guard_falls_back_on_device(be):
+    """operands outside the guard (rows scaled by 1e-30, Inf) are flagged by the split kernel and the
+    product is done by the conditional mixed-split launches: componentwise accuracy as the mixed
+    split's, non-finite values propagate like numpy's, and a fused relu output of a fallback product
+    still feeds the next product (statistics recomputed on demand).  All-zero operands are safe."""
+    rng = np.random.RandomState(1)
+    M, N, K = 512, 384, 512
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    a[::2] *= np.float32(1e-30)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "f16"
+    try:
+        da, db = be.from_numpy(a), be.from_numpy(b)
+        z, act = be.matmul(da, db, act=True)
+        assert _meta(da.split["f"][3])["safe"] == 0 and _meta(db.split["f"][3])["safe"] == 1
+        a64, b64 = a.astype(np.float64), b.astype(np.float64)
+        comp = np.max(np.abs(z.numpy() - a64 @ b64) / (np.abs(a64) @ np.abs(b64)))
+        assert comp <= 5e-6, comp
+        assert _meta(act.split["stat"])["need_stats"] == 1
+        w2 = rng.standard_normal((N, 128)).astype(np.float32)
+        nxt = be.matmul(act, be.from_numpy(w2)).numpy()
+        assert _meta(act.split["f"][3])["absmax"] == np.max(np.maximum(z.numpy(), 0))
+        ref2 = np.maximum(z.numpy().astype(np.float64), 0) @ w2.astype(np.float64)
+        comp2 = np.max(np.abs(nxt - ref2) / (np.maximum(z.numpy().astype(np.float64), 0) @ np.abs(w2.astype(np.float64)) + 1e-300))
+        assert comp2 <= 5e-6, comp2
+        bad = rng.standard_normal((M, K)).astype(np.float32)
+        bad[3, 5] = np.inf
+        out = be.matmul(be.from_numpy(bad), db).numpy()
+        assert np.all(~np.isfinite(out[3])) and np.all(np.isfinite(np.delete(out, 3, axis=0)))
+        zero = be.matmul(be.from_numpy(np.zeros((M, K), np.float32)), db)
+        assert np.all(zero.numpy() == 0)
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+
+
+def test_f16_tensor_relative_bound(be):
+    """the documented limit of the default split: an element further than 19 binades below its
+    tensor's largest is held to 2^-39 of that largest, not to 2^-20 of itself.  One row in 512 scaled
+    by 2^-25 stays inside the guard (1/512 of the non-zeros); its entries meet
+    |err| <= 2^-19 (|A| @ |B|) + 2^-38 max|A| sum_k |b_kj| and every other row the componentwise 5e-6"""
+    rng = np.random.RandomState(2)
+    M, N, K = 512, 256, 512
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    a[7] *= np.float32(2.0 ** -25)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "f16"
+    try:
+        da = be.from_numpy(a)
+        c = be.matmul(da, be.from_numpy(b)).numpy().astype(np.float64)
+        assert _meta(da.split["f"][3])["safe"] == 1
+    finally:
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    err = np.abs(c - a64 @ b64)
+    comp = np.abs(a64) @ np.abs(b64)
+    bound = 2.0 ** -19 * comp + 2.0 ** -38 * np.max(np.abs(a64)) * np.sum(np.abs(b64), axis=0)[None, :]
+    assert np.all(err <= bound)
+    others = np.delete(np.arange(M), 7)
+    assert np.max(err[others] / comp[others]) <= 5e-6
+
+
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("ks", [2, 4])
 def test_tf32x3_ordered_split_k(be, cg, ks):
@@ -166,8 +336,8 @@ def test_tf32x3_ordered_split_k(be, cg, ks):
     c0 = rng.standard_normal((M, N)).astype(np.float32)
     da, db, dbias = be.from_numpy(a), be.from_numpy(b), be.from_numpy(bias)
     ref = _ref(a, b, False, False, bias) + c0
-    old = be.TC_MIN_MNK
-    be.TC_MIN_MNK = 0
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "mix"
     be.set_gemm_cta_group(cg)
     be.set_gemm_ksplit(ks)
     try:
@@ -181,7 +351,7 @@ def test_tf32x3_ordered_split_k(be, cg, ks):
     finally:
         be.set_gemm_ksplit(0)
         be.set_gemm_cta_group(0)
-        be.TC_MIN_MNK = old
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
 
 
 def test_tf32x3_better_than_plain_tf32(be):

@@ -553,7 +553,7 @@ def test_grouped_dense_backward_matches_separate_launches(dtype):
         assert op_cases.rel_err(b, 2 * a) <= 10 * tol                # second backward doubled it
 
 
-@pytest.mark.parametrize("split", ["mix", "tf32x3"])
+@pytest.mark.parametrize("split", ["f16", "mix", "tf32x3"])
 def test_tensor_core_mlp_teacher_forced_over_steps(split):
     """the tcgen05 path along a training run: 12 steps of a 3-layer 256-wide MLP at batch 512, the
     oracle's (Adam-updated, float32-rounded) parameters loaded into the engine before every step,

@@ -59,7 +59,7 @@ def _engine_model(init):
     return net, Model(net=net, loss=SoftmaxCrossEntropyLoss(), optimizer=Adam(lr=1e-3))
 
 
-@pytest.mark.parametrize("split", ["mix", "tf32x3"])
+@pytest.mark.parametrize("split", ["f16", "mix", "tf32x3"])
 def test_wide_mlp_step_matches_oracle(wide_case, split):
     import core._backend as be
     from core.tensor import Tensor
@@ -157,7 +157,7 @@ def _componentwise_err(c, a64, b64):
     return float(np.max(np.abs(c.astype(np.float64) - exact) / np.maximum(scale, 1e-300)))
 
 
-@pytest.mark.parametrize("split", ["mix", "tf32x3"])
+@pytest.mark.parametrize("split", ["f16", "mix", "tf32x3"])
 @pytest.mark.parametrize("case", ["wide_exponents", "cancellation", "tiny_and_huge_rows", "bf16_unfriendly"])
 def test_operand_split_on_adversarial_data(split, case):
     """The default operand split (TF32 main term + two BF16 cross terms) on data chosen to hurt it:
@@ -199,4 +199,6 @@ def test_operand_split_on_adversarial_data(split, case):
         be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
     assert np.all(np.isfinite(c))
     err = _componentwise_err(c, a.astype(np.float64), b.astype(np.float64))
-    assert err <= (5e-6 if split == "mix" else 2e-6), (case, split, err)
+    # ("f16", the default: wide_exponents and tiny_and_huge_rows are outside its guard and are done
+    # by the on-device fallback to the mixed split; the other two run on the fp16 planes)
+    assert err <= (2e-6 if split == "tf32x3" else 5e-6), (case, split, err)

@@ -251,6 +251,37 @@ def test_operand_split_error_model():
         em = S.rel_err(S.product_mix(a, b), exact)
         e1 = S.rel_err(S.product_single_tf32(a, b), exact)
         assert e3 <= 1.5e-7 and em <= 1e-6 and e1 >= 20 * em, (e3, em, e1)
+        # the scaled fp16 hi/lo split (gemm_f16.cu, the default): 22 bits per element, error of the
+        # dropped lo*lo term only -- at least as good as the mixed split
+        ef = S.rel_err(S.product_f16(a, b), exact)
+        assert ef <= 3e-7 and ef <= em, (ef, em)
+        assert S.f16_guard(a) and S.f16_guard(b)
+
+
+def test_f16_split_element_bound_and_guard():
+    """gemm_f16.cu's element bound |x - (hf + l) 2^-e| <= 2^-20 max(|x|, 2^-19 max|X|) on data with a
+    wide range, and its guard: ordinary tensors pass, rows on wildly different scales, exponents
+    spread over tens of binades and non-finite values do not"""
+    import split_error_model as S
+    rng = np.random.RandomState(3)
+    x = (rng.standard_normal((256, 512)) * np.exp2(rng.randint(-24, 1, (256, 512)))).astype(np.float32)
+    hf, l, e = S.f16_planes(x)
+    assert 2.0 ** 14 <= np.max(np.abs(np.ldexp(x, e))) < 2.0 ** 15
+    err = np.abs(np.ldexp((hf.astype(np.float64) + l), -e) - x)
+    bound = 2.0 ** -20 * np.maximum(np.abs(x), 2.0 ** -19 * np.max(np.abs(x)))
+    assert np.all(err <= bound)
+    assert np.all(np.isfinite(hf)) and np.all(np.isfinite(l))
+    g = rng.standard_normal((512, 512)).astype(np.float32)
+    assert S.f16_guard(g) and S.f16_guard(np.maximum(g, 0)) and S.f16_guard(np.zeros((4, 4), np.float32))
+    rows = g * np.where(np.arange(512) % 2 == 0, 1e-30, 1.0)[:, None].astype(np.float32)
+    assert not S.f16_guard(rows)
+    assert not S.f16_guard((g * np.exp2(rng.randint(-30, 31, g.shape))).astype(np.float32))
+    bad = g.copy()
+    bad[3, 4] = np.inf
+    assert not S.f16_guard(bad)
+    one_small_row = g.copy()
+    one_small_row[7] *= np.float32(2.0 ** -25)       # 1/512 of the elements: inside the guard
+    assert S.f16_guard(one_small_row)
 
 
 def test_allreduce_chunk_bounds():
