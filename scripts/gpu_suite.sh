@@ -18,7 +18,7 @@ for s in $STAGES; do
     mnist) timeout 600 python bench.py --workload mnist --steps 2000 --warmup 50 > gpurun_out/bench_mnist.log 2>&1; timeout 600 python bench.py --workload mnist --steps 2000 --warmup 50 --graph off --no-cpu-baseline > gpurun_out/bench_mnist_eager.log 2>&1 ;;
     sweep) timeout 900 python scripts/sweep_ops.py --cpu > gpurun_out/sweep.json 2> gpurun_out/sweep.err ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_list.log 2>&1 ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 22 -c 3 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_gemm.log 2>&1; ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2>/dev/null; [ $(stat -c %s gpurun_out/prof_gemm.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/prof_gemm.ncu-rep ;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_f16x3 -s 22 -c 3 -f -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_gemm.log 2>&1; ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2>/dev/null; [ $(stat -c %s gpurun_out/prof_gemm.ncu-rep) -gt 20000000 ] && rm -f gpurun_out/prof_gemm.ncu-rep ;;
     dist)  timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_dist.log 2>&1 ;;
     bench_n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.log 2>&1 ;;
     bench_n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 30 --warmup 5 > gpurun_out/bench_n4.log 2>&1 ;;

@@ -269,6 +269,33 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             continue;
           }
+#ifdef TNN_F16_PREFETCH
+          if (kb + TNN_F16_PREFETCH < kb_end) {
+            // pull the boxes of a later K block into L2 now, so that the load that fills the stage
+            // then is an L2 hit rather than a DRAM round trip
+            const int kp = (kb + TNN_F16_PREFETCH) * BK;
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int j = 0; j < ROWS / 64; ++j) {
+                tma_prefetch_l2_2d(&map_a_l, row_a + 64 * j, kp);
+                tma_prefetch_l2_2d(&map_a_h, row_a + 64 * j, kp);
+              }
+            } else {
+              tma_prefetch_l2_2d(&map_a_l, kp, row_a);
+              tma_prefetch_l2_2d(&map_a_h, kp, row_a);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < ROWS / 64; ++j) {
+                tma_prefetch_l2_2d(&map_b_h, row_b + 64 * j, kp);
+                tma_prefetch_l2_2d(&map_b_l, row_b + 64 * j, kp);
+              }
+            } else {
+              tma_prefetch_l2_2d(&map_b_h, kp, row_b);
+              tma_prefetch_l2_2d(&map_b_l, kp, row_b);
+            }
+          }
+#endif
           if constexpr (A_MN) {
 #pragma unroll
             for (int j = 0; j < ROWS / 64; ++j) {
