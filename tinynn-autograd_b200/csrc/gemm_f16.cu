@@ -58,7 +58,15 @@ constexpr int PLANE_BYTES = ROWS * BK * 2;   // 16 KB
 constexpr int STAGE_BYTES = 4 * PLANE_BYTES; // A.hf, A.l, B.hf, B.l
 constexpr int STAGES = TNN_F16_STAGES;
 constexpr int CHUNK_KB = 256 / BK;           // 256 k per TMEM accumulator chunk (as gemm_tc.cu)
-constexpr int NUM_THREADS = 384;
+#ifndef TNN_F16_THREADS
+#define TNN_F16_THREADS 384
+#endif
+// 384 threads: warpgroup 0 = TMA producer warp, MMA issuer warp, 2 idle warps (setmaxnreg.dec 40);
+// warpgroups 1-2 = epilogue (setmaxnreg.inc 216: 128 tile sums + a 32-column TMEM chunk per thread).
+// (TNN_F16_THREADS=320 -- ten warps, no setmaxnreg -- was tried to give ptxas a larger launch-time
+// budget: registers are allocated per 4 warps, so the budget stays 168 and the spills grow.)
+constexpr int NUM_THREADS = TNN_F16_THREADS;
+constexpr int EPI_WARP0 = NUM_THREADS == 320 ? 2 : 4;   // first epilogue warp
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int EPI_PATCH_BYTES = 8 * 4096;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_PATCH_BYTES;
@@ -243,7 +251,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
 
   if (warp == 0) {
     // ================= TMA producer =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (NUM_THREADS == 384) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -325,7 +333,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (NUM_THREADS == 384) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc(0, 0, A_MN, B_MN);      // f16 x f16 -> f32
       int stage = 0;
@@ -395,13 +403,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
                clock64() - t_begin, w_full, w_empty);
 #endif
     }
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else if (warp < EPI_WARP0) {
+    if constexpr (NUM_THREADS == 384) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else {
     // ================= epilogue =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    if constexpr (NUM_THREADS == 384) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32): fixed by warp id % 4
+    const int half = (warp - EPI_WARP0) >> 2;        // accumulator columns [128*half, 128*half+128)
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool relu = flags & 2;
@@ -469,7 +477,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         // the store loop; a fully unrolled version was 8,000 SASS instructions that every warp
         // walked once per tile, instruction-fetch-bound at ~40 k cycles per tile).
         const int row_base = tm * TILE_M + (int)cta_rank * ROWS + quad * 32;
-        float4* patch = reinterpret_cast<float4*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
+        float4* patch = reinterpret_cast<float4*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - EPI_WARP0) * 256;
         const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
         const bool act_aligned = !emit_act || (((reinterpret_cast<uintptr_t>(act_out) |
                                                   reinterpret_cast<uintptr_t>(mask_src)) & 15) == 0);
