@@ -175,7 +175,12 @@ __device__ __forceinline__ void patch_write(const float (&sum)[128], float4* pat
 }
 
 // flags: 1 accumulate into D, 2 ReLU in place, 8 statistics of relu(D) instead of D
-template <bool A_MN, bool B_MN>
+// CL = 2: one CTA pair per tile.  CL = 4: a cluster of two pairs on adjacent tile columns (tm, 2j)
+// and (tm, 2j+1); they need the same A rows, so each CTA fetches only half of its A tile and TMA
+// multicasts it to its counterpart in the other pair (A's L2->SM traffic halves: 48 KB instead of
+// 64 KB per CTA per K block).  Both pairs then move through the K blocks in lock-step: a stage is
+// refilled when BOTH pairs' MMAs have released it (empty barriers count two commits).
+template <bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_constant__ CUtensorMap map_a_l,
                   const __grid_constant__ CUtensorMap map_b_h, const __grid_constant__ CUtensorMap map_b_l,
@@ -199,8 +204,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
+  const uint32_t cl_rank = cluster_ctarank();          // 0..CL-1
+  const uint32_t pair = cl_rank >> 1;                  // which tile column of the cluster's two
+  const uint32_t cta_rank = cl_rank & 1u;              // rank inside the CTA pair
   const bool leader = cta_rank == 0;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_h);
@@ -209,7 +217,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
     tma_prefetch_desc(&map_b_l);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL / 2);   // one tcgen05.commit per pair that reads (or feeds) this stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -228,10 +236,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
 
   const int tiles_m = (M + TILE_M - 1) / TILE_M;
   const int tiles_n = (N + UMMA_N - 1) / UMMA_N;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_ns = CL == 4 ? (tiles_n + 1) / 2 : tiles_n;   // scheduling units per tile row
+  const int num_tiles = tiles_m * tiles_ns;
   const int num_kb = (K + BK - 1) / BK;
-  const int group = blockIdx.x / 2;
-  const int num_groups = gridDim.x / 2;
+  const int group = blockIdx.x / CL;
+  const int num_groups = gridDim.x / CL;
   // work units: whole-K tiles [0, t_full), then the ragged last wave cut into tail_split K ranges
   // (fixed-order read-modify-write behind a per-tile arrival counter, see gemm_tc.cu)
   const int tail_rem = num_tiles - t_full;
@@ -259,9 +268,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         int t, sp, kb_begin, kb_end;
         decode(u, t, sp, kb_begin, kb_end);
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
+        tile_coords(t, tiles_m, tiles_ns, group_m, tm, tn);
+        if constexpr (CL == 4) tn = 2 * tn + (int)pair;
         const int row_a = tm * TILE_M + (int)cta_rank * ROWS;
-        const int row_b = tn * UMMA_N + (int)cta_rank * ROWS;
+        const int row_b = tn * UMMA_N + (int)cta_rank * ROWS;   // (beyond N for the odd pair of a ragged row: zero fill)
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa_h = smem_base + stage * STAGE_BYTES;
@@ -304,7 +314,20 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
             }
           }
 #endif
-          if constexpr (A_MN) {
+          if constexpr (CL == 4) {
+            // this CTA's half (64 rows: 8 KB per plane) of the A tile, to itself and to the CTA of the
+            // same pair rank in the other pair; the other half arrives from there
+            const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2)));
+            const uint32_t off = pair * (uint32_t)(PLANE_BYTES / 2);
+            const int ra = row_a + 64 * (int)pair;
+            if constexpr (A_MN) {
+              tma_load_2d_pair_mc(sa_l + off, &map_a_l, full_bar(stage), ra, k0, mc);
+              tma_load_2d_pair_mc(sa_h + off, &map_a_h, full_bar(stage), ra, k0, mc);
+            } else {
+              tma_load_2d_pair_mc(sa_l + off, &map_a_l, full_bar(stage), k0, ra, mc);
+              tma_load_2d_pair_mc(sa_h + off, &map_a_h, full_bar(stage), k0, ra, mc);
+            }
+          } else if constexpr (A_MN) {
 #pragma unroll
             for (int j = 0; j < ROWS / 64; ++j) {
               tma_load_2d<2>(sa_l + j * MN_BOX_BYTES, &map_a_l, full_bar(stage), row_a + 64 * j, k0);
@@ -384,13 +407,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
               umma_bf16<2>(tmem_d, da_h, db_l, idesc, 1u);
               umma_bf16<2>(tmem_d, da_h, db_h, idesc, 1u);
             }
-            umma_commit<2>(empty_bar(stage));
+            umma_commit_pair_mask(empty_bar(stage), CL == 4 ? (uint16_t)15 : (uint16_t)3);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit<2>(tfull_bar(acc));
+          umma_commit_pair_mask(tfull_bar(acc), pair_mask);
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1u;
@@ -427,7 +450,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
       const bool want_stats = stat_out != nullptr && final_unit;
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_n, group_m, tm, tn);
+      tile_coords(t, tiles_m, tiles_ns, group_m, tm, tn);
+      if constexpr (CL == 4) tn = 2 * tn + (int)pair;
+      const bool tile_valid = tn < tiles_n;            // (the odd pair of a ragged tile row computes zeros)
+      const int flag_idx = tm * tiles_n + tn;
       const int col0 = tn * UMMA_N + half * 128;
       float sum[128];
 #pragma unroll
@@ -447,19 +473,19 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_bar(acc), 2 * pair);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
-      if (sp > 0) {
+      if (sp > 0 && tile_valid) {
         if (lane == 0) {
           const unsigned int need = (unsigned int)(sp * 16);
           unsigned int seen;
           long long t0 = clock64();
           do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tile_flags + t) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tile_flags + flag_idx) : "memory");
             if (clock64() - t0 > 8000000000LL) {
               printf("tnn gemm_f16: split-K ordering wait timed out (tile %d split %d)\n", t, sp);
               __trap();
@@ -588,10 +614,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
           __syncwarp();
         }
       }
-      if (u >= t_full && sp + 1 < tail_split) {
+      if (u >= t_full && sp + 1 < tail_split && tile_valid) {
         __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(tile_flags + t, 1u);
+        if (lane == 0) atomicAdd(tile_flags + flag_idx, 1u);
       }
     }
     if (stat_out != nullptr) {
@@ -729,12 +755,12 @@ static int get_encode_fn() {
 // 16-bit plane.  K-major [rows, K] (pitch ld): box {64 k, 128 rows}.  MN-major [K, rows] (pitch
 // ld): box {64 mn, 64 k}.  128-byte swizzle both ways.
 static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld,
-                    bool mn_major) {
+                    bool mn_major, int box_rows = ROWS) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) TNN_FAIL("f16 GEMM: operand plane must be 16-byte aligned");
   if (ld % 8 != 0) TNN_FAIL("f16 GEMM: operand pitch must be a multiple of 8 elements");
   cuuint64_t dims[2] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 64 : BK), (cuuint32_t)(mn_major ? BK : ROWS)};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? 64 : BK), (cuuint32_t)(mn_major ? BK : box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -747,28 +773,35 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, 
 
 static unsigned int* g_tile_flags = nullptr;
 constexpr int MAX_FLAG_TILES = 1 << 16;
-static bool g_attr_set[2][2] = {};
-static int g_group_m = -8;     // tile rasterisation: panels of 8 tile columns measured 1-2 % ahead of row-major; (TNN_F16_GROUP_M), see tile_coords
+static bool g_attr_set[2][2][2] = {};
+static int g_group_m = -8;     // tile rasterisation: panels of 8 tile columns measured 1-2 % ahead of row-major;
+                               // (TNN_F16_GROUP_M), see tile_coords
+static int g_cluster = 2;      // 2: CTA pairs (default).  4: two pairs per cluster sharing A by TMA multicast
+                               // (TNN_F16_CLUSTER=4): correct, -6 % time per tile round, but only 33 such
+                               // clusters are co-resident on B200's 148 SMs (132 SMs busy, 8 rounds instead of
+                               // 7 for 512 tiles), so it measures 3-20 % slower overall
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int CL>
 static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64_t lda, const void* b_h,
                   const void* b_l, int64_t ldb, int64_t M, int64_t N, int64_t K, const float* bias,
                   int flags, float* act_out, const float* mask_src, const Meta* meta_a,
                   const Meta* meta_b, Meta* stat_out) {
   CUtensorMap ma_h, ma_l, mb_h, mb_l;
-  if (make_map(&ma_h, a_h, M, K, lda, A_MN)) return 1;
-  if (make_map(&ma_l, a_l, M, K, lda, A_MN)) return 1;
+  // (CL = 4: a CTA fetches half of its A tile -- 64 rows -- and receives the other half by multicast)
+  if (make_map(&ma_h, a_h, M, K, lda, A_MN, CL == 4 ? 64 : ROWS)) return 1;
+  if (make_map(&ma_l, a_l, M, K, lda, A_MN, CL == 4 ? 64 : ROWS)) return 1;
   if (make_map(&mb_h, b_h, N, K, ldb, B_MN)) return 1;
   if (make_map(&mb_l, b_l, N, K, ldb, B_MN)) return 1;
-  auto kern = gemm_f16x3_kernel<A_MN, B_MN>;
-  if (!g_attr_set[A_MN][B_MN]) {
+  auto kern = gemm_f16x3_kernel<A_MN, B_MN, CL>;
+  if (!g_attr_set[A_MN][B_MN][CL == 4]) {
     TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_attr_set[A_MN][B_MN] = true;
+    g_attr_set[A_MN][B_MN][CL == 4] = true;
   }
-  const int64_t tiles = ceil_div(M, TILE_M) * ceil_div(N, UMMA_N);
-  const int max_groups = std::max(1, ctx().sm_count / 2);
+  const int64_t tiles_m = ceil_div(M, TILE_M), tiles_n = ceil_div(N, UMMA_N);
+  const int64_t tiles = tiles_m * (CL == 4 ? ceil_div(tiles_n, 2) : tiles_n);   // scheduling units
+  const int max_groups = std::max(1, ctx().sm_count / CL);
   int t_full = (int)tiles, tail_split = 1;
-  if (!(flags & 2) && tiles <= MAX_FLAG_TILES) {
+  if (!(flags & 2) && tiles_m * tiles_n <= MAX_FLAG_TILES) {
     const int64_t num_kb = ceil_div(K, BK);
     const int64_t rem = tiles % max_groups;
     if (rem > 0) {
@@ -782,28 +815,53 @@ static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64
   }
   if (tail_split > 1) {
     if (!g_tile_flags) TNN_CUDA(cudaMalloc(&g_tile_flags, MAX_FLAG_TILES * sizeof(unsigned int)));
-    TNN_CUDA(cudaMemsetAsync(g_tile_flags, 0, (size_t)tiles * sizeof(unsigned int), ctx().stream));
+    TNN_CUDA(cudaMemsetAsync(g_tile_flags, 0, (size_t)(tiles_m * tiles_n) * sizeof(unsigned int), ctx().stream));
   }
   const int64_t units = t_full + (tiles - t_full) * tail_split;
   const int groups = (int)std::min<int64_t>(units, max_groups);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(groups * 2));
+  cfg.gridDim = dim3((unsigned)(groups * CL));
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = ctx().stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (CL == 4) {
+    // a persistent grid must be co-resident: 4-CTA clusters do not tile every GPC (B200: 33 of the
+    // 37 that 148 SMs would hold), and a cluster that cannot start waits for a whole one to finish
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      TNN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) max_clusters = 1;
+    }
+    if (groups > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * CL));
+  }
+  // rasterisation knob in scheduling units: a panel of g tile columns = g/2 units when CL = 4
+  const int gm = (CL == 4 && g_group_m < 0) ? std::min(-1, g_group_m / 2) : g_group_m;
   prof_begin(1);
   TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_h, ma_l, mb_h, mb_l, D, ldd, (int)M, (int)N, (int)K, bias, flags,
-                              t_full, tail_split, g_tile_flags, act_out, mask_src, meta_a, meta_b, stat_out, g_group_m));
+                              t_full, tail_split, g_tile_flags, act_out, mask_src, meta_a, meta_b, stat_out, gm));
   ctx().launches++;
   prof_end(1);
   return 0;
+}
+
+template <int CL>
+static int launch_layout(int layout, float* D, int64_t ldd, const void* a_h, const void* a_l, int64_t lda,
+                         const void* b_h, const void* b_l, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                         const float* bias, int flags, float* act_out, const float* mask_src,
+                         const Meta* ma, const Meta* mb, Meta* st) {
+  switch (layout & 3) {
+    case 0: return launch<false, false, CL>(D, ldd, a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    case 1: return launch<true, false, CL>(D, ldd, a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    case 2: return launch<false, true, CL>(D, ldd, a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+    default: return launch<true, true, CL>(D, ldd, a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+  }
 }
 
 }  // namespace f16
@@ -877,17 +935,17 @@ int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, i
   if (!env_read) {
     const char* gm = getenv("TNN_F16_GROUP_M");
     if (gm && atoi(gm) != 0 && atoi(gm) >= -64 && atoi(gm) <= 64) f16::g_group_m = atoi(gm);
+    const char* cl = getenv("TNN_F16_CLUSTER");
+    if (cl && (atoi(cl) == 2 || atoi(cl) == 4)) f16::g_cluster = atoi(cl);
     env_read = true;
   }
   const f16::Meta* ma = (const f16::Meta*)a_meta;
   const f16::Meta* mb = (const f16::Meta*)b_meta;
   f16::Meta* st = (f16::Meta*)stat_meta;
-  switch (layout & 3) {
-    case 0: return f16::launch<false, false>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
-    case 1: return f16::launch<true, false>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
-    case 2: return f16::launch<false, true>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
-    default: return f16::launch<true, true>(D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
-  }
+  // two pairs per cluster only pay when there are at least two tile columns to share A over
+  if (f16::g_cluster == 4 && N > f16::UMMA_N)
+    return f16::launch_layout<4>(layout, D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
+  return f16::launch_layout<2>(layout, D, ldd, a_hf, a_l16, lda, b_hf, b_l16, ldb, M, N, K, bias, flags, act_out, mask_src, ma, mb, st);
 }
 
 }  // extern "C"

@@ -95,6 +95,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
   }
 }
+// cta_group::2 tile load multicast to the CTAs of `mask` (same CTA-relative destination and barrier
+// offset in each; with the peer bit cleared the signal lands on each destination pair's leader)
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                    int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// tcgen05.commit of a CTA pair, arrival multicast to the CTAs of `mask`
+__device__ __forceinline__ void umma_commit_pair_mask(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
 // L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
