@@ -478,7 +478,7 @@ def run_b200_arm(args, cfg):
     del xs
     e2e_steps = args.steps
     feed = iter(PrefetchIterator(batch_size=B, loop=True, num_classes=C)(x_data, y_data))
-    for _ in range(2):                                   # e2e warm-up
+    for _ in range(max(args.warmup, n_host_batches + 1)):   # e2e warm-up: every host batch has crossed PCIe once
         batch = next(feed)
         float(stepper(batch.inputs, batch.targets).values)
     dist.barrier()

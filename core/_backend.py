@@ -104,6 +104,7 @@ _SIGNATURES = {
                              _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp,
                              _c_i64, _c_vp],
     "tnn_f16_stats": [_c_vp, _c_i64, _c_vp, _c_int],
+    "tnn_set_gemm_f16_cluster": [_c_int],
     "tnn_f16_meta_reset": [_c_vp],
     "tnn_split_f16": [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_gemm_f16x3": [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64,
@@ -123,7 +124,7 @@ _SIGNATURES = {
     "tnn_ce_merge_stats": [_c_int, _c_vp, _c_vp, _c_int],
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
     "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
-    "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp],
+    "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp],
     "tnn_set_gemm_reserved_sms": [_c_int],
     "tnn_d2h_async": [_c_vp, _c_vp, _c_sz, _c_vp],
     "tnn_event_sync": [_c_vp],
@@ -941,6 +942,12 @@ def set_gemm_cta_group(cg):
         _raise("tnn_set_gemm_cta_group")
 
 
+def set_gemm_f16_cluster(cl):
+    load_library()
+    if _lib.tnn_set_gemm_f16_cluster(int(cl)):
+        _raise("tnn_set_gemm_f16_cluster")
+
+
 def set_gemm_ksplit(ks):
     load_library()
     if _lib.tnn_set_gemm_ksplit(int(ks)):
@@ -1141,9 +1148,17 @@ def ce_bwd(z, y, stats, q, m_global, g):
     dz = empty((B, C), z.dtype)
     if g.dtype != z.dtype:
         g = astype(g, z.dtype)
+    # a gradient this large feeds tensor-core products: the kernel also records max|dz| for their split
+    stat = None
+    if z.dtype == F32 and TC_SPLIT == "f16" and TC_ENABLED and B * C >= (1 << 16):
+        stat = _new_meta()
+        if _lib.tnn_f16_meta_reset(stat.ptr):
+            _raise("tnn_f16_meta_reset")
     if _lib.tnn_ce_bwd(_DT_CODE[z.dtype], dz.ptr, z.ptr, _DT_CODE[y.dtype], y.ptr, B, C, stats.ptr,
-                       q.ptr, float(m_global), g.ptr):
+                       q.ptr, float(m_global), g.ptr, stat.ptr if stat is not None else None):
         _raise("tnn_ce_bwd")
+    if stat is not None:
+        dz.split = {"epoch": _split_epoch, "stat": stat}
     return dz
 
 

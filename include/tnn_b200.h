@@ -264,6 +264,10 @@ int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
  * tnn_f16_stats_cond, launched before the next split of that result, then computes them (it returns
  *   at once otherwise). */
 int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode);
+/* cluster shape of tnn_gemm_f16x3: 2 = one CTA pair per tile (default); 4 = two pairs on adjacent tile
+ * columns sharing their A rows by TMA multicast (fewer operand bytes, but only 33 such clusters are
+ * co-resident on B200: measured slower, kept as an option; also TNN_F16_CLUSTER). */
+int tnn_set_gemm_f16_cluster(int cl);
 int tnn_f16_meta_reset(void* meta);
 int tnn_split_f16(const float* x, int64_t R, int64_t C, void* hf, void* l16, int64_t ld, void* meta,
                   int relu_mode);
@@ -319,7 +323,9 @@ int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B,
 int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                      double m_global, void* stats_dev, void* q_dev, void* loss_dev);
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev);
+               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev,
+               void* stat_meta /* optional, float32: a zeroed f16 operand record (tnn_f16_meta_reset)
+                                  that receives max|dz| for the next tnn_split_f16 */);
 
 /* Small-MLP tail in ONE launch (examples/mnist/run.py:59-84 at batch 128: layers 2..L of the
  * 784-200-100-70-30-10 network).  Phase 1, 4 batch rows per CTA with the tail's weights resident in

@@ -227,6 +227,36 @@ def test_f16_gemm_shapes(be, shape):
         be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
 
 
+@pytest.mark.parametrize("shape", [(256, 512, 128), (384, 768, 200), (300, 300, 96), (1000, 520, 260),
+                                   (2048, 1024, 512), (512, 1280, 4100)])
+def test_f16_gemm_multicast_clusters(be, shape):
+    """optional cluster shape of the default kernel: two CTA pairs on adjacent tile columns share
+    their A rows by TMA multicast (odd tile-column counts leave the second pair of the last cluster
+    without a tile).  Bit-identical to the pair kernel: same products, same order."""
+    M, N, K = shape
+    old, old_split = be.TC_MIN_MNK, be.TC_SPLIT
+    be.TC_MIN_MNK, be.TC_SPLIT = 0, "f16"
+    try:
+        rng = np.random.RandomState(M + 5 * N + K)
+        a = rng.standard_normal((M, K)).astype(np.float32)
+        b = rng.standard_normal((K, N)).astype(np.float32)
+        bias = rng.standard_normal((1, N)).astype(np.float32)
+        at, bt = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)
+        res = {}
+        for cl in (2, 4):
+            be.set_gemm_f16_cluster(cl)
+            da, db = be.from_numpy(a), be.from_numpy(b)
+            res[cl] = [be.matmul(da, db, bias=be.from_numpy(bias)).numpy(),
+                       be.matmul(da, be.from_numpy(bt), tb=True).numpy(),
+                       be.matmul(be.from_numpy(at), db, ta=True).numpy()]
+        assert op_cases.rel_err(res[4][0], _ref(a, b, False, False, bias)) <= TOL
+        for x, y in zip(res[2], res[4]):
+            assert np.array_equal(x, y)
+    finally:
+        be.set_gemm_f16_cluster(2)
+        be.TC_MIN_MNK, be.TC_SPLIT = old, old_split
+
+
 def test_f16_fused_outputs(be):
     """act=True on the default path: the launch stores the pre-activation and records max|relu(z)| for
     the next split (the fp32 activation is a LazyReLU, never written); the next product consumes it.

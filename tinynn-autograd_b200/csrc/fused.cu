@@ -390,12 +390,13 @@ ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats
 template <typename T, typename TY, bool VEC>
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats, const T* q,
-              T m, const T* gptr) {
+              T m, const T* gptr, unsigned int* absmax_out) {
   // rows over blockIdx.y, column slots over blockIdx.x * 256 + threadIdx.x: no per-element division.
   // VEC: a slot is 4 consecutive columns moved with 128-bit (z, dz) / 128- or 256-bit (y) accesses.
   constexpr int W = VEC ? 4 : 1;
   const T mx = stats[0], S = stats[1], g = gptr[0];
   const int64_t nslot = C / W;
+  unsigned int amax = 0u;   // bits of max |dz| (float32 only): the operand statistics of the next split
   for (int64_t r = blockIdx.y; r < B; r += gridDim.y) {
     const T qm = q[r] * m;
     const T* zr = z + r * C;
@@ -424,9 +425,16 @@ ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* sta
         T v = p;
         if (yv[k] != T(0)) v = p - (yv[k] * p) / qm;
         out[k] = g * v;
+        if constexpr (sizeof(T) == 4) amax = max(amax, __float_as_uint((float)out[k]) & 0x7FFFFFFFu);
       }
       if constexpr (VEC) *reinterpret_cast<float4*>(dr + c * 4) = make_float4(out[0], out[1], out[2], out[3]);
       else dr[c] = out[0];
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    if (absmax_out != nullptr) {      // integer max: exact and order-independent
+      amax = __reduce_max_sync(0xFFFFFFFFu, amax);
+      if ((threadIdx.x & 31) == 0 && amax) atomicMax(absmax_out, amax);
     }
   }
 }
@@ -632,7 +640,7 @@ static int ce_loss_impl(const T* z, const TY* y, int64_t B, int64_t C, const T* 
 
 template <typename T, typename TY>
 static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats,
-                       const T* q, double m, const T* g) {
+                       const T* q, double m, const T* g, unsigned int* absmax_out) {
   cudaStream_t st = ctx().stream;
   // the 128-bit path is float32 logits with 4-column-aligned rows
   const bool vec = sizeof(T) == 4 && (C % 4 == 0) && al16(dz) && al16(z) && al16(y);
@@ -642,9 +650,9 @@ static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, con
   if (gy > 65535) gy = 65535;
   if (vec) {
     if constexpr (sizeof(T) == 4)
-      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out);
   } else {
-    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g);
+    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out);
   }
   TNN_POST_LAUNCH();
   return 0;
@@ -726,17 +734,20 @@ int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64
 }
 
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev) {
+               const void* stats_dev, const void* q_dev, double m_global, const void* g_dev,
+               void* stat_meta) {
   TNN_REQUIRE_INIT();
   if (B <= 0 || C <= 0) return 0;
+  unsigned int* am = (unsigned int*)stat_meta;   // word 0 of an f16 operand record (gemm_f16.cu)
+  if (am && dtype != TNN_F32) TNN_FAIL("tnn_ce_bwd: operand statistics are float32 only");
   if (dtype == TNN_F32 && y_dtype == TNN_F32)
-    return ce_bwd_impl<float, float>((float*)dz, (const float*)z, (const float*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev);
+    return ce_bwd_impl<float, float>((float*)dz, (const float*)z, (const float*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am);
   if (dtype == TNN_F32 && y_dtype == TNN_F64)
-    return ce_bwd_impl<float, double>((float*)dz, (const float*)z, (const double*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev);
+    return ce_bwd_impl<float, double>((float*)dz, (const float*)z, (const double*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am);
   if (dtype == TNN_F64 && y_dtype == TNN_F64)
-    return ce_bwd_impl<double, double>((double*)dz, (const double*)z, (const double*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev);
+    return ce_bwd_impl<double, double>((double*)dz, (const double*)z, (const double*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am);
   if (dtype == TNN_F64 && y_dtype == TNN_F32)
-    return ce_bwd_impl<double, float>((double*)dz, (const double*)z, (const float*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev);
+    return ce_bwd_impl<double, float>((double*)dz, (const double*)z, (const float*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am);
   TNN_FAIL("tnn_ce_bwd: bad dtype");
 }
 

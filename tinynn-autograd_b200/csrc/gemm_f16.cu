@@ -871,6 +871,12 @@ using namespace tnn;
 
 extern "C" {
 
+int tnn_set_gemm_f16_cluster(int cl) {
+  if (cl != 2 && cl != 4) TNN_FAIL("tnn_set_gemm_f16_cluster: 2 (CTA pairs) or 4 (two pairs sharing A by TMA multicast)");
+  f16::g_cluster = cl;
+  return 0;
+}
+
 int tnn_f16_stats(const float* x, int64_t n, void* meta, int relu_mode) {
   TNN_REQUIRE_INIT();
   if (!meta) TNN_FAIL("tnn_f16_stats: meta is required");
