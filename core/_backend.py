@@ -755,7 +755,10 @@ def scatter_flat(g, idx_dev, shape):
 # --------------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------------
-TC_MIN_MNK = int(os.environ.get("TNN_TC_MIN_MNK", str(1 << 26)))
+# below this M*N*K the SIMT kernel is at least as fast as the tensor-core path with its operand
+# passes (statistics, split, product, two conditional launches: ~58 us of launches for fresh operands
+# against 13-54 us of SIMT GEMM up to 2^29; scripts/tc_threshold.py, profiles/r02f_tc_threshold.txt)
+TC_MIN_MNK = int(os.environ.get("TNN_TC_MIN_MNK", str(1 << 29)))
 TC_ENABLED = os.environ.get("TNN_TC", "1") != "0"
 TC_MN_MAJOR = os.environ.get("TNN_TC_MN_MAJOR", "1") != "0"   # 0: transposed tf32 planes instead
 # operand split of the tensor-core product: "mix" = tf32 main term + bf16 cross terms (default),

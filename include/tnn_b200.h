@@ -240,17 +240,18 @@ int tnn_gemm_tf32_bf16x2(float* D, int64_t ldd,
                          const float* mask_src);
 /* Scaled two-plane split (the default path since r02): the 3xTF32 expansion with every factor in 16
  * bits.  X = x * 2^e (one e per tensor: max|X| in [2^14, 2^15)), hf = fp16(X) (the mantissa tf32
- * keeps), l = bf16(X - hf);
+ * keeps), l = fp16(X - hf);
  *     A*B ~= 2^-(ea+eb) * ( l_A*hf_B + hf_A*l_B + hf_A*hf_B )
- * as three tcgen05 kind::f16 MMAs per K=16 step (f16 and bf16 operands mixed) on 4 B/element of
- * planes.  Element error <= 2^-20 * max(|x|, 2^-28 max|X_tensor|); replaces ops.py:150-160 `@`.
- * Each operand carries a 16-byte device record `meta` {u32 bits of max|x|, u32 ~bits of the min
- * non-zero |x|, i32 e, i32 safe}:
- * tnn_f16_stats      zeroes the record and fills the two statistics of x (relu_mode: of relu(x)).
+ * as three tcgen05 kind::f16 MMAs per K=16 step on 4 B/element of planes.  Element error
+ * <= 2^-20 * max(|x|, 2^-19 max|x_tensor|); replaces ops.py:150-160 `@`.
+ * Each operand carries a 32-byte device record `meta` {u32 bits of max|x|, u32 statistics-missing
+ * flag, i32 e, i32 safe, u32 small-element count, u32 non-zero count, u32 ticket, u32 pad}:
+ * tnn_f16_stats      zeroes the record and fills max|x| (relu_mode: of relu(x)).
  * tnn_f16_meta_reset zeroes a record a producer kernel is about to fill (tnn_gemm_f16x3 stat_meta).
- * tnn_split_f16      derives e and `safe` from the statistics (safe = finite, and no non-zero
- *                    element more than 40 binades below the largest) and, when safe, writes the planes
- *                    (pitch ld, multiple of 8, pad columns zeroed).
+ * tnn_split_f16      derives e from max|x|, writes the planes (pitch ld, multiple of 8, pad columns
+ *                    zeroed) and, from what it counts while writing, `safe`: the tensor is finite and at
+ *                    most 1/256 of its non-zero elements lie below 2^-5 after scaling (the level under
+ *                    which the residual plane goes subnormal).
  * tnn_gemm_f16x3     layout bits / flags 1, 2 as tnn_gemm_tf32x3; returns at once ON THE DEVICE
  *                    unless both operands are safe.  act_out (optional) = relu(D), or with mask_src
  *                    D * (mask_src >= 0) (ops.py:336-343 fused into the dX product).  stat_meta

@@ -221,16 +221,21 @@ def test_captured_tensor_core_step_is_bit_identical():
     """256-wide layers at batch 1024: every product is above the tensor-core threshold"""
     import core._backend as be
     widths = [256, 256, 256]
-    assert be.use_tensor_cores(1024, 256, 256, be.F32)
-    batches = _batches(0, 256, 256, [1024] * 6)
-    net_a, model_a = _model(widths, 5, d_in=256)
-    net_b, model_b = _model(widths, 5, d_in=256)
-    for x, y in batches:
-        la = float(_eager(model_a, x, y).values)
-        lb = float(model_b.train_step(x, y).values)
-        assert la == lb
-    for pa, pb in zip(_params(net_a), _params(net_b)):
-        assert np.array_equal(pa, pb)
+    old = be.TC_MIN_MNK
+    be.TC_MIN_MNK = 1 << 26
+    try:
+        assert be.use_tensor_cores(1024, 256, 256, be.F32)
+        batches = _batches(0, 256, 256, [1024] * 6)
+        net_a, model_a = _model(widths, 5, d_in=256)
+        net_b, model_b = _model(widths, 5, d_in=256)
+        for x, y in batches:
+            la = float(_eager(model_a, x, y).values)
+            lb = float(model_b.train_step(x, y).values)
+            assert la == lb
+        for pa, pb in zip(_params(net_a), _params(net_b)):
+            assert np.array_equal(pa, pb)
+    finally:
+        be.TC_MIN_MNK = old
 
 
 def test_replay_does_not_touch_other_tensors():

@@ -70,6 +70,10 @@ constexpr int EPI_WARP0 = NUM_THREADS == 320 ? 2 : 4;   // first epilogue warp
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int EPI_PATCH_BYTES = 8 * 4096;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_PATCH_BYTES;
+#ifndef TNN_F16_KBOX_ROWS
+#define TNN_F16_KBOX_ROWS 128
+#endif
+constexpr int KBOX_ROWS = TNN_F16_KBOX_ROWS;   // rows per TMA box of a K-major plane (BK = 64: 128-byte rows)
 constexpr int MN_BOX_BYTES = 64 * BK * 2;    // one {64 mn, 64 k} box
 constexpr float SMALL_LIMIT = 0.03125f;      // 2^-5: below it the residual plane is subnormal
 constexpr unsigned int GUARD_FRACTION = 256; // unsafe when small non-zeros * 256 > non-zeros
@@ -334,8 +338,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
               tma_load_2d<2>(sa_h + j * MN_BOX_BYTES, &map_a_h, full_bar(stage), row_a + 64 * j, k0);
             }
           } else {
-            tma_load_2d<2>(sa_l, &map_a_l, full_bar(stage), k0, row_a);
-            tma_load_2d<2>(sa_h, &map_a_h, full_bar(stage), k0, row_a);
+#pragma unroll
+            for (int j = 0; j < ROWS / KBOX_ROWS; ++j) {
+              tma_load_2d<2>(sa_l + j * KBOX_ROWS * 128, &map_a_l, full_bar(stage), k0, row_a + j * KBOX_ROWS);
+              tma_load_2d<2>(sa_h + j * KBOX_ROWS * 128, &map_a_h, full_bar(stage), k0, row_a + j * KBOX_ROWS);
+            }
           }
           if constexpr (B_MN) {
 #pragma unroll
@@ -344,8 +351,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
               tma_load_2d<2>(sb_l + j * MN_BOX_BYTES, &map_b_l, full_bar(stage), row_b + 64 * j, k0);
             }
           } else {
-            tma_load_2d<2>(sb_h, &map_b_h, full_bar(stage), k0, row_b);
-            tma_load_2d<2>(sb_l, &map_b_l, full_bar(stage), k0, row_b);
+#pragma unroll
+            for (int j = 0; j < ROWS / KBOX_ROWS; ++j) {
+              tma_load_2d<2>(sb_h + j * KBOX_ROWS * 128, &map_b_h, full_bar(stage), k0, row_b + j * KBOX_ROWS);
+              tma_load_2d<2>(sb_l + j * KBOX_ROWS * 128, &map_b_l, full_bar(stage), k0, row_b + j * KBOX_ROWS);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -788,10 +798,10 @@ static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64
                   const Meta* meta_b, Meta* stat_out) {
   CUtensorMap ma_h, ma_l, mb_h, mb_l;
   // (CL = 4: a CTA fetches half of its A tile -- 64 rows -- and receives the other half by multicast)
-  if (make_map(&ma_h, a_h, M, K, lda, A_MN, CL == 4 ? 64 : ROWS)) return 1;
-  if (make_map(&ma_l, a_l, M, K, lda, A_MN, CL == 4 ? 64 : ROWS)) return 1;
-  if (make_map(&mb_h, b_h, N, K, ldb, B_MN)) return 1;
-  if (make_map(&mb_l, b_l, N, K, ldb, B_MN)) return 1;
+  if (make_map(&ma_h, a_h, M, K, lda, A_MN, CL == 4 ? 64 : KBOX_ROWS)) return 1;
+  if (make_map(&ma_l, a_l, M, K, lda, A_MN, CL == 4 ? 64 : KBOX_ROWS)) return 1;
+  if (make_map(&mb_h, b_h, N, K, ldb, B_MN, KBOX_ROWS)) return 1;
+  if (make_map(&mb_l, b_l, N, K, ldb, B_MN, KBOX_ROWS)) return 1;
   auto kern = gemm_f16x3_kernel<A_MN, B_MN, CL>;
   if (!g_attr_set[A_MN][B_MN][CL == 4]) {
     TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -479,7 +479,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-          else mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);   // publishes no memory: no MEMBAR (see gemm_f16.cu)
         }
         if (++acc == 2) {
           acc = 0;
