@@ -154,6 +154,29 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tn = r / rows;
 }
 
+// registers -> swizzled patch for the 32-column block CB of a thread's 128 sums (+ bias)
+template <int CB>
+__device__ __forceinline__ void patch_write_tc(const float (&sum)[128], float4* patch, int lane,
+                                               const float* bias_u, int colb, int N) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float4 v = make_float4(sum[CB * 32 + c4 * 4], sum[CB * 32 + c4 * 4 + 1], sum[CB * 32 + c4 * 4 + 2],
+                           sum[CB * 32 + c4 * 4 + 3]);
+    if (bias_u) {
+      const int c = colb + c4 * 4;
+      if (c + 3 < N) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_u + c);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      } else {
+        if (c < N) v.x += bias_u[c];
+        if (c + 1 < N) v.y += bias_u[c + 1];
+        if (c + 2 < N) v.z += bias_u[c + 2];
+      }
+    }
+    patch[lane * 8 + (c4 ^ (lane & 7))] = v;
+  }
+}
+
 // ---- the GEMM kernel ---------------------------------------------------------------------------
 // MIX = false: planes are (hi, lo) tf32, map_*_lo = the lo plane, map_*_l16 unused.
 // MIX = true : planes are (hi tf32, h16 = bf16(x), l16 = bf16(x - hi)); map_*_lo = h16.
@@ -515,6 +538,45 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         const bool rows_aligned = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
         const bool act_aligned = !emit_act || (((reinterpret_cast<uintptr_t>(act_out) |
                                                   reinterpret_cast<uintptr_t>(mask_src)) & 15) == 0);
+        if (!accumulate && !emit_act && rows_aligned) {
+          // plain tile (bias / in-place ReLU only): ONE rolled copy of the store loop.  The general
+          // form below is fully unrolled -- thousands of SASS instructions that a warp walks once
+          // per tile, instruction-fetch-bound (r02, gemm_f16.cu) -- and is kept for the launches
+          // that read back (accumulate, mask) or emit operand planes.
+          const int rr = lane >> 3, c4l = lane & 7;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            const int colb = col0 + cb * 32;
+            if (colb >= N) break;                               // warp-uniform
+            switch (cb) {                                       // register indices are compile-time
+              case 0: patch_write_tc<0>(sum, patch, lane, bias_u, colb, N); break;
+              case 1: patch_write_tc<1>(sum, patch, lane, bias_u, colb, N); break;
+              case 2: patch_write_tc<2>(sum, patch, lane, bias_u, colb, N); break;
+              default: patch_write_tc<3>(sum, patch, lane, bias_u, colb, N); break;
+            }
+            __syncwarp();
+            const int gcol = colb + c4l * 4;
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + rr, grow = row_base + r;
+              if (grow >= M) break;
+              float4 v = patch[r * 8 + (c4l ^ (r & 7))];
+              if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              float* dp = D + (int64_t)grow * ldd + gcol;
+              if (gcol + 3 < N) {
+                *reinterpret_cast<float4*>(dp) = v;
+              } else {
+                if (gcol < N) dp[0] = v.x;
+                if (gcol + 1 < N) dp[1] = v.y;
+                if (gcol + 2 < N) dp[2] = v.z;
+              }
+            }
+            __syncwarp();
+          }
+        } else
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           const int colb = col0 + cb * 32;                      // first column of this 32-wide block
