@@ -179,42 +179,27 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
       const float* __restrict__ wg = a.w[l];
       float* ws = sm + a.w_s[l];
       const int total = K * N;
-      if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(wg) & 15) == 0) {
-        // all of a thread's 128-bit loads are issued before the first store (one L2 round trip per
-        // batch, not one per element group); (row, column) of the first element by one division per
-        // vector, then incrementally.  (A warp-per-row variant with 4-byte loads and no division at
-        // all measured slower: 29k against 16k cycles for the 119 KB of the MNIST tail.)
-        constexpr int SB = 8;
-        const int nq = total / 4;
-        for (int q0 = tid; q0 < nq; q0 += THREADS * SB) {
-          float4 v[SB];
-#pragma unroll
-          for (int u = 0; u < SB; ++u) {
-            const int q = q0 + u * THREADS;
-            if (q < nq) v[u] = reinterpret_cast<const float4*>(wg)[q];
-          }
-#pragma unroll
-          for (int u = 0; u < SB; ++u) {
-            const int q = q0 + u * THREADS;
-            if (q < nq) {
-              int k = (q * 4) / N, j = (q * 4) - k * N;
-              const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                ws[k * pitch + j] = e[t];
-                if (++j == N) { j = 0; ++k; }
-              }
-            }
-          }
-        }
-      } else {
+      // 4-byte cp.async per element (the odd pitch rules out wider ones): every element of the layer
+      // is in flight at once and nothing passes through registers; (row, column) advance
+      // incrementally by the constant stride, no division per element.  (r02: batches of eight
+      // 128-bit loads followed by scalar stores took 16 k cycles for the 119 KB of the MNIST tail.)
+      {
+        const int dk = THREADS / N, dj = THREADS - dk * N;
+        int k = tid / N, j = tid - k * N;
         for (int q = tid; q < total; q += THREADS) {
-          const int k = q / N;
-          ws[k * pitch + (q - k * N)] = wg[q];
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ws + k * pitch + j);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wg + q) : "memory");
+          j += dj;
+          k += dk;
+          if (j >= N) { j -= N; ++k; }
         }
       }
       for (int j = tid; j < N; j += THREADS) sm[a.b_s[l] + j] = a.b[l][j];
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#ifdef TNN_MLP_TIMING
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     TNN_PROBE();   // 1: weights staged
     // ---- the CTA's rows of z1 (pre-activation of the first layer) and a1 = relu(z1) ----
     {
@@ -229,6 +214,7 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
         as[k] = relu4(zs[k]);
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the weights (in flight since the top) have landed
     __syncthreads();
     float4* scratch = reinterpret_cast<float4*>(sm + a.scratch_s);
 
