@@ -851,17 +851,29 @@ def split_planes_f16(x):
 
 
 _FALLBACK_PLANES = {}
+_FALLBACK_CAP_BYTES = 16 << 30     # many distinct product shapes in one process: start over past this
+_fallback_bytes = 0
 
 
 def _fallback_planes(role, R, ld):
-    """scratch for the conditional mixed split behind an f16 product (stream-ordered reuse)"""
+    """scratch for the conditional mixed split behind an f16 product.  Outside a capture: one set per
+    (role, shape), reused by every later product of that shape (same stream: ordered) and never
+    returned to the pool, so nothing that was enqueued can find it recycled under it.  While a step is
+    being recorded the planes are fresh blocks, which belong to the graph until it is destroyed (a
+    recorded conditional split must not point at scratch that eager products also use)."""
+    if _capturing:
+        return (empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld))
+    global _fallback_bytes
     key = (role, R, ld)
     p = _FALLBACK_PLANES.get(key)
     if p is None:
-        if len(_FALLBACK_PLANES) >= 16:
+        if _fallback_bytes > _FALLBACK_CAP_BYTES:
+            sync()                       # nothing enqueued points at the old sets any more
             _FALLBACK_PLANES.clear()
+            _fallback_bytes = 0
         p = (empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld))
         _FALLBACK_PLANES[key] = p
+        _fallback_bytes += 8 * R * ld
     return p
 
 
