@@ -272,7 +272,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         int t, sp, kb_begin, kb_end;
         decode(u, t, sp, kb_begin, kb_end);
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_ns, group_m, tm, tn);
+        tile_coords((flags & 32) ? num_tiles - 1 - t : t, tiles_m, tiles_ns, group_m, tm, tn);
         if constexpr (CL == 4) tn = 2 * tn + (int)pair;
         const int row_a = tm * TILE_M + (int)cta_rank * ROWS;
         const int row_b = tn * UMMA_N + (int)cta_rank * ROWS;   // (beyond N for the odd pair of a ragged row: zero fill)
@@ -460,7 +460,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
       const bool want_stats = stat_out != nullptr && final_unit;
       const float* bias_u = sp == 0 ? bias : nullptr;
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_ns, group_m, tm, tn);
+      tile_coords((flags & 32) ? num_tiles - 1 - t : t, tiles_m, tiles_ns, group_m, tm, tn);
       if constexpr (CL == 4) tn = 2 * tn + (int)pair;
       const bool tile_valid = tn < tiles_n;            // (the odd pair of a ragged tile row computes zeros)
       const int flag_idx = tm * tiles_n + tn;
@@ -786,6 +786,9 @@ constexpr int MAX_FLAG_TILES = 1 << 16;
 static bool g_attr_set[2][2][2] = {};
 static int g_group_m = -8;     // tile rasterisation: panels of 8 tile columns measured 1-2 % ahead of row-major;
                                // (TNN_F16_GROUP_M), see tile_coords
+static bool g_reverse = true;  // tiles in descending order (TNN_F16_REVERSE=0: ascending): the product starts on
+                               // the rows the split pass wrote last (still in L2) and ends on the rows the next
+                               // split pass reads first; measured 8.33 -> 8.20 ms/step (same box, 3 runs each)
 static int g_cluster = 2;      // 2: CTA pairs (default).  4: two pairs per cluster sharing A by TMA multicast
                                // (TNN_F16_CLUSTER=4): correct, -6 % time per tile round, but only 33 such
                                // clusters are co-resident on B200's 148 SMs (132 SMs busy, 8 rounds instead of
@@ -951,10 +954,13 @@ int tnn_gemm_f16x3(float* D, int64_t ldd, const void* a_hf, const void* a_l16, i
   if (!env_read) {
     const char* gm = getenv("TNN_F16_GROUP_M");
     if (gm && atoi(gm) != 0 && atoi(gm) >= -64 && atoi(gm) <= 64) f16::g_group_m = atoi(gm);
+    const char* rv = getenv("TNN_F16_REVERSE");
+    if (rv) f16::g_reverse = atoi(rv) != 0;
     const char* cl = getenv("TNN_F16_CLUSTER");
     if (cl && (atoi(cl) == 2 || atoi(cl) == 4)) f16::g_cluster = atoi(cl);
     env_read = true;
   }
+  if (f16::g_reverse) flags |= 32;
   const f16::Meta* ma = (const f16::Meta*)a_meta;
   const f16::Meta* mb = (const f16::Meta*)b_meta;
   f16::Meta* st = (f16::Meta*)stat_meta;
