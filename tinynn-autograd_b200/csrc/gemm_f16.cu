@@ -39,6 +39,9 @@
 #include "tc_ptx.cuh"
 
 namespace tnn {
+namespace tc {
+extern int g_reserved_sms;   // tnn_set_gemm_reserved_sms (gemm_tc.cu)
+}
 namespace f16 {
 
 using namespace tnn::tc;
@@ -812,7 +815,7 @@ static int launch(float* D, int64_t ldd, const void* a_h, const void* a_l, int64
   }
   const int64_t tiles_m = ceil_div(M, TILE_M), tiles_n = ceil_div(N, UMMA_N);
   const int64_t tiles = tiles_m * (CL == 4 ? ceil_div(tiles_n, 2) : tiles_n);   // scheduling units
-  const int max_groups = std::max(1, ctx().sm_count / CL);
+  const int max_groups = std::max(1, (ctx().sm_count - tc::g_reserved_sms) / CL);
   int t_full = (int)tiles, tail_split = 1;
   if (!(flags & 2) && tiles_m * tiles_n <= MAX_FLAG_TILES) {
     const int64_t num_kb = ceil_div(K, BK);

@@ -918,7 +918,7 @@ static int g_group_m = 1;                      // tile rasterisation group; meas
 static int g_force_ksplit = 0;                 // 0 = auto (tail split), 1 = off, 2/4 = every tile (TNN_GEMM_KSPLIT)
 static int g_force_cg = 0;  // 0 = default, 1 / 2 = forced (TNN_GEMM_CG or tnn_set_gemm_cta_group)
 static bool g_attr_set[3][2][2][2] = {};
-static int g_reserved_sms = 0;   // SMs the persistent grid leaves to other streams (NCCL)
+int g_reserved_sms = 0;          // SMs the persistent grids leave to other streams (NCCL); also read by gemm_f16.cu
 static int g_exp_flags = 0;  // timing experiments (TNN_EXP_*): OR-ed into the kernel's flags
 
 struct ActOut {
