@@ -454,6 +454,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
     const int ec = -(meta_a->exp + meta_b->exp);
     const float f1 = pow2f(ec / 2), f2 = pow2f(ec - ec / 2);
     unsigned int st_max = 0u;
+#ifdef TNN_F16_PROBE
+    long long ep_wait = 0, ep_store = 0;
+    const long long ep_begin = clock64();
+#endif
     for (int u = group; u < num_units; u += num_groups) {
       int t, sp, kb_begin, kb_end;
       decode(u, t, sp, kb_begin, kb_end);
@@ -472,7 +476,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.f;
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += CHUNK_KB) {
+#ifdef TNN_F16_PROBE
+        const long long q0 = clock64();
+#endif
         mbar_wait(tfull_bar(acc), acc_phase);
+#ifdef TNN_F16_PROBE
+        ep_wait += clock64() - q0;
+#endif
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
                                (uint32_t)(acc * UMMA_N + half * 128);
@@ -508,6 +518,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
         __syncwarp();
         __threadfence();
       }
+#ifdef TNN_F16_PROBE
+      const long long q1 = clock64();
+#endif
       {
         // ---- store the tile.  Each warp bounces its 32 x 32 blocks through a private 4 KB swizzled
         // shared-memory patch and comes back with 8 lanes per row, so every global access is 4 full
@@ -538,41 +551,61 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
           const int gcol = colb + c4l * 4;
           if (rows_aligned && act_aligned && colb + 32 <= N) {
             if (pre_src == nullptr) {
-              // plain / relu / statistics: nothing to read back
-#pragma unroll 1
+              // plain / relu / statistics: nothing to read back.  Unrolled with everything that does
+              // not change hoisted: per row group one 128-bit shared-memory load at a constant
+              // offset, one 128-bit store through a running pointer (a rolled version that
+              // rebuilt its indices every iteration spent ~21 k cycles per tile here).
+              const int nrows = min(32, M - row_base);          // rows of this warp's block inside M
+              const float4* pp0 = patch + rr * 8 + (c4l ^ rr);              // rows rr, rr+8, ...  (r & 7 = rr)
+              const float4* pp1 = patch + (rr + 4) * 8 + (c4l ^ (rr + 4));  // rows rr+4, rr+12, ... (r & 7 = rr+4)
+              float* dp = D + (int64_t)(row_base + rr) * ldd + gcol;
+              float* ap = emit_act ? act_out + (int64_t)(row_base + rr) * ldd + gcol : nullptr;
+              const int64_t step = 4 * ldd;
+#pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + rr, grow = row_base + r;
-                if (grow >= M) break;
-                float4 v = patch[r * 8 + (c4l ^ (r & 7))];
-                if (relu) {
-                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
-                  v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                if (4 * i + rr < nrows) {
+                  float4 v = (i & 1) ? pp1[(i >> 1) * 64] : pp0[(i >> 1) * 64];
+                  if (relu) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+                    v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                  }
+                  *reinterpret_cast<float4*>(dp) = v;
+                  if (want_relu_side) {                        // ReLU(D), NaN-propagating like np.clip
+                    v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+                    v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+                    if (emit_act) *reinterpret_cast<float4*>(ap) = v;
+                  }
+                  if (want_stats)
+                    st_max = max(max(st_max, __float_as_uint(v.x) & 0x7FFFFFFFu),
+                                 max(max(__float_as_uint(v.y) & 0x7FFFFFFFu, __float_as_uint(v.z) & 0x7FFFFFFFu),
+                                     __float_as_uint(v.w) & 0x7FFFFFFFu));
                 }
-                *reinterpret_cast<float4*>(D + (int64_t)grow * ldd + gcol) = v;
-                if (want_relu_side) {                          // ReLU(D), NaN-propagating like np.clip
-                  v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
-                  v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
-                  if (emit_act) *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = v;
-                }
-                if (want_stats)
-                  st_max = max(max(st_max, __float_as_uint(v.x) & 0x7FFFFFFFu),
-                               max(max(__float_as_uint(v.y) & 0x7FFFFFFFu, __float_as_uint(v.z) & 0x7FFFFFFFu),
-                                   __float_as_uint(v.w) & 0x7FFFFFFFu));
+                dp += step;
+                if (emit_act) ap += step;
               }
             } else {
               // accumulate-into-D and / or the ReLU-backward mask: whatever has to be READ first is
               // fetched for all 8 row groups up front (8 independent 128-bit loads in flight)
+              const int nrows = min(32, M - row_base);
+              const float4* pp0 = patch + rr * 8 + (c4l ^ rr);
+              const float4* pp1 = patch + (rr + 4) * 8 + (c4l ^ (rr + 4));
+              const int64_t off0 = (int64_t)(row_base + rr) * ldd + gcol, step = 4 * ldd;
               float4 pre[8];
+              {
+                const float* sp_ = pre_src + off0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int grow = row_base + 4 * i + rr;
-                if (grow < M) pre[i] = *reinterpret_cast<const float4*>(pre_src + (int64_t)grow * ldd + gcol);
+                for (int i = 0; i < 8; ++i) {
+                  if (4 * i + rr < nrows) pre[i] = *reinterpret_cast<const float4*>(sp_);
+                  sp_ += step;
+                }
               }
+              float* dp = D + off0;
+              float* ap = emit_act ? act_out + off0 : nullptr;
+              const float* mp = (want_mask && accumulate) ? mask_src + off0 : nullptr;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + rr, grow = row_base + r;
-                if (grow < M) {
-                  float4 v = patch[r * 8 + (c4l ^ (r & 7))];
+                if (4 * i + rr < nrows) {
+                  float4 v = (i & 1) ? pp1[(i >> 1) * 64] : pp0[(i >> 1) * 64];
                   if (accumulate) {
                     v.x += pre[i].x; v.y += pre[i].y; v.z += pre[i].z; v.w += pre[i].w;
                   }
@@ -580,24 +613,25 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
                     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
                     v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                   }
-                  *reinterpret_cast<float4*>(D + (int64_t)grow * ldd + gcol) = v;
+                  *reinterpret_cast<float4*>(dp) = v;
                   if (want_mask) {
                     // act = D * (pre-activation >= 0): the ReLU gradient mask of ops.py:336-343
-                    const float4 z = accumulate
-                        ? *reinterpret_cast<const float4*>(mask_src + (int64_t)grow * ldd + gcol)
-                        : pre[i];
+                    const float4 z = accumulate ? *reinterpret_cast<const float4*>(mp) : pre[i];
                     v.x = z.x >= 0.f ? v.x : v.x * 0.f; v.y = z.y >= 0.f ? v.y : v.y * 0.f;
                     v.z = z.z >= 0.f ? v.z : v.z * 0.f; v.w = z.w >= 0.f ? v.w : v.w * 0.f;
                   } else if (want_relu_side) {
                     v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
                     v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
                   }
-                  if (emit_act) *reinterpret_cast<float4*>(act_out + (int64_t)grow * ldd + gcol) = v;
+                  if (emit_act) *reinterpret_cast<float4*>(ap) = v;
                   if (want_stats)
                     st_max = max(max(st_max, __float_as_uint(v.x) & 0x7FFFFFFFu),
                                  max(max(__float_as_uint(v.y) & 0x7FFFFFFFu, __float_as_uint(v.z) & 0x7FFFFFFFu),
                                      __float_as_uint(v.w) & 0x7FFFFFFFu));
                 }
+                dp += step;
+                if (emit_act) ap += step;
+                if (mp) mp += step;
               }
             }
           } else {
@@ -627,12 +661,20 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_h, const __grid_cons
           __syncwarp();
         }
       }
+#ifdef TNN_F16_PROBE
+      ep_store += clock64() - q1;
+#endif
       if (u >= t_full && sp + 1 < tail_split && tile_valid) {
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(tile_flags + flag_idx, 1u);
       }
     }
+#ifdef TNN_F16_PROBE
+    if ((group == 0 || group == 37) && warp == 4 && lane == 0 && cta_rank == 0)
+      printf("probe group %d epilogue warp 4: total %lld cycles, waiting for a chunk %lld, storing tiles %lld\n",
+             group, clock64() - ep_begin, ep_wait, ep_store);
+#endif
     if (stat_out != nullptr) {
       // integer max is exact and order-independent: the record does not depend on timing
       st_max = __reduce_max_sync(0xFFFFFFFFu, st_max);
