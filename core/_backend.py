@@ -786,8 +786,8 @@ def _round8(n):
     return (n + 7) // 8 * 8
 
 
-def _empty_bf16(rows, ld):
-    """raw bf16 plane (kept as a float32 DArray of half the width for bookkeeping)"""
+def _empty_16bit(rows, ld):
+    """raw 16-bit plane, bf16 or fp16 (kept as a float32 DArray of half the width for bookkeeping)"""
     return empty((rows, ld // 2), F32)
 
 
@@ -801,7 +801,7 @@ def split_planes_mix(x):
         return cache["m"]
     R, C = x.shape
     ld = _round8(C)
-    hi, h16, l16 = empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld)
+    hi, h16, l16 = empty((R, ld), F32), _empty_16bit(R, ld), _empty_16bit(R, ld)
     if _lib.tnn_split_tf32_bf16(x.ptr, R, C, hi.ptr, h16.ptr, l16.ptr, ld):
         _raise("tnn_split_tf32_bf16")
     cache["m"] = (hi, h16, l16, ld)
@@ -841,7 +841,7 @@ def split_planes_f16(x):
         # (the producer's epilogue normally recorded them; this launch only works when the producer
         # was the fallback product, which records none)
         _raise("tnn_f16_stats_cond")
-    hf, l16 = _empty_bf16(R, ld), _empty_bf16(R, ld)
+    hf, l16 = _empty_16bit(R, ld), _empty_16bit(R, ld)
     if _lib.tnn_split_f16(src.ptr, R, C, hf.ptr, l16.ptr, ld, meta.ptr, relu_mode):
         _raise("tnn_split_f16")
     # (the source is not stored when it is x itself: x -> x.split -> x would be a reference cycle,
@@ -862,7 +862,7 @@ def _fallback_planes(role, R, ld):
     being recorded the planes are fresh blocks, which belong to the graph until it is destroyed (a
     recorded conditional split must not point at scratch that eager products also use)."""
     if _capturing:
-        return (empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld))
+        return (empty((R, ld), F32), _empty_16bit(R, ld), _empty_16bit(R, ld))
     global _fallback_bytes
     key = (role, R, ld)
     p = _FALLBACK_PLANES.get(key)
@@ -871,7 +871,7 @@ def _fallback_planes(role, R, ld):
             sync()                       # nothing enqueued points at the old sets any more
             _FALLBACK_PLANES.clear()
             _fallback_bytes = 0
-        p = (empty((R, ld), F32), _empty_bf16(R, ld), _empty_bf16(R, ld))
+        p = (empty((R, ld), F32), _empty_16bit(R, ld), _empty_16bit(R, ld))
         _FALLBACK_PLANES[key] = p
         _fallback_bytes += 8 * R * ld
     return p
@@ -1020,7 +1020,7 @@ def matmul(a, b, ta=False, tb=False, bias=None, out=None, accumulate=False, relu
         ld_act = _round8(N)
         if act:
             act_hi = empty((M, ld_act), F32)
-            act_h16, act_l16 = _empty_bf16(M, ld_act), _empty_bf16(M, ld_act)
+            act_h16, act_l16 = _empty_16bit(M, ld_act), _empty_16bit(M, ld_act)
             if LAZY_RELU_OUT and mask_src is None:
                 act_out = LazyReLU(out)      # planes only: the fp32 activation is not written
         if _lib.tnn_gemm_tf32_bf16x2(out.ptr, N, a_hi.ptr, a_h16.ptr, a_l16.ptr, lda, b_hi.ptr,
