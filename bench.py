@@ -74,17 +74,33 @@ def read_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs"""
+    """SM clock and throttle reasons sampled while the timed region runs: NVML queried from a
+    thread of this process every 20 ms (no start-up latency, so even a 0.2 s region at 8 ranks gets
+    samples); `nvidia-smi -lms 100` in a subprocess if NVML cannot be opened"""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.lines = []          # nvidia-smi: csv lines; NVML: (sm_mhz, max_mhz, reason bitmask)
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
@@ -95,6 +111,19 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                          getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                mask = int(reasons(self._handle)) if reasons else 0
+                self.lines.append((sm, self._max, mask))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
@@ -104,33 +133,46 @@ class ClockSampler(object):
         return len(self.lines)
 
     def stop(self, first=0, last=None):
-        if self.proc is None:
+        if self.nvml is None and self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        window = self.lines[first:last] or self.lines[-3:]
-        for ln in window:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.nvml is not None:
+            nv = self.nvml
+            self._stop.set()
+            self.thread.join(timeout=2)
+            bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+            for s_mhz, m_mhz, mask in (self.lines[first:last] or self.lines[-3:]):
+                sm.append(s_mhz)
+                mx.append(m_mhz)
+                for nm, bit in zip(self.NAMES, bits):
+                    if mask & bit:
+                        reasons.add(nm)
+            source = "nvml, 20 ms period"
+        else:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            for ln in (self.lines[first:last] or self.lines[-3:]):
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(self.NAMES, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            source = "nvidia-smi -lms 100"
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         busy = [s for s in sm if s > 0]
         return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)),
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source=source)
 
 
 def make_config(cfg, batch_per_gpu, world):

@@ -122,9 +122,10 @@ _SIGNATURES = {
     "tnn_colsum": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
     "tnn_ce_stats": [_c_int, _c_vp, _c_i64, _c_i64, _c_vp],
     "tnn_ce_merge_stats": [_c_int, _c_vp, _c_vp, _c_int],
-    "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp],
+    "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp, _c_vp],
     "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
-    "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp],
+    "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp,
+                   _c_vp],
     "tnn_set_gemm_reserved_sms": [_c_int],
     "tnn_d2h_async": [_c_vp, _c_vp, _c_sz, _c_vp],
     "tnn_event_sync": [_c_vp],
@@ -396,6 +397,46 @@ class LazyRows(DArray):
         if self._real is None:
             self._real = gather_rows(self._src, self._idx, self.shape[0])
         return self._real
+
+    @property
+    def ptr(self):
+        return self._materialise().ptr
+
+    @property
+    def buf(self):
+        return self._materialise().buf
+
+    def view(self, shape, offset_elems=0):
+        return self._materialise().view(shape, offset_elems)
+
+
+class LazyOneHot(DArray):
+    """(n, C) float32 one-hot rows named by n int32 class indices on the device; written
+    (tnn_one_hot, run.py:27-28 get_one_hot) only if somebody asks for their address.  The fused
+    cross-entropy takes the indices themselves (ops.softmax_ce_), so in a training step fed by
+    utils.data_iterator.PrefetchIterator the dense label matrix -- 134 MB per batch for the wide
+    MLP -- is neither written nor read."""
+    __slots__ = ("_labels", "_dst", "_real")
+
+    def __init__(self, labels, n_classes, dst):
+        self._labels = labels            # device vector of n int32 indices (kept in a 4-byte float view)
+        self._dst = dst                  # (n, C) float32 array that receives the rows on demand
+        self._real = None
+        self.shape = (labels.shape[0], int(n_classes))
+        self.dtype = F32
+        self.size = _prod(self.shape)
+        self.split = None
+        self.aux = None
+
+    def _materialise(self):
+        if self._real is None:
+            one_hot_into(self._dst, self._labels.ptr, self.shape[0], self.shape[1])
+            self._real = self._dst
+        return self._real
+
+    @property
+    def labels_ptr(self):
+        return self._labels.ptr
 
     @property
     def ptr(self):
@@ -1134,12 +1175,21 @@ def ce_merge_stats(stats_all, n_ranks):
     return out
 
 
+def _ce_labels(y):
+    """(dense pointer, class-index pointer): a one-hot matrix that exists only as indices is passed as
+    indices"""
+    if type(y) is LazyOneHot and y._real is None:
+        return None, y.labels_ptr
+    return y.ptr, None
+
+
 def ce_loss(z, y, stats, m_global):
     B, C = z.shape
     q = empty((B,), z.dtype)
     loss = empty((), z.dtype)
-    if _lib.tnn_ce_loss(_DT_CODE[z.dtype], z.ptr, _DT_CODE[y.dtype], y.ptr, B, C, stats.ptr,
-                        float(m_global), q.ptr, loss.ptr):
+    y_ptr, lab_ptr = _ce_labels(y)
+    if _lib.tnn_ce_loss(_DT_CODE[z.dtype], z.ptr, _DT_CODE[y.dtype], y_ptr, B, C, stats.ptr,
+                        float(m_global), q.ptr, loss.ptr, lab_ptr):
         _raise("tnn_ce_loss")
     return loss, q
 
@@ -1169,8 +1219,9 @@ def ce_bwd(z, y, stats, q, m_global, g):
         stat = _new_meta()
         if _lib.tnn_f16_meta_reset(stat.ptr):
             _raise("tnn_f16_meta_reset")
-    if _lib.tnn_ce_bwd(_DT_CODE[z.dtype], dz.ptr, z.ptr, _DT_CODE[y.dtype], y.ptr, B, C, stats.ptr,
-                       q.ptr, float(m_global), g.ptr, stat.ptr if stat is not None else None):
+    y_ptr, lab_ptr = _ce_labels(y)
+    if _lib.tnn_ce_bwd(_DT_CODE[z.dtype], dz.ptr, z.ptr, _DT_CODE[y.dtype], y_ptr, B, C, stats.ptr,
+                       q.ptr, float(m_global), g.ptr, stat.ptr if stat is not None else None, lab_ptr):
         _raise("tnn_ce_bwd")
     if stat is not None:
         dz.split = {"epoch": _split_epoch, "stat": stat}

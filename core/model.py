@@ -403,6 +403,9 @@ class _CapturedStep(object):
         for dst, src in ((self.x, x._data), (self.y, y._data)):
             if isinstance(src, be.LazyRows) and src._real is None:
                 src.gather_into(dst)        # rows perm[start:end] straight into the graph's input
+            elif isinstance(src, be.LazyOneHot) and src._real is None:
+                # class indices -> one-hot rows written straight into the graph's label buffer
+                be.one_hot_into(dst, src.labels_ptr, src.shape[0], src.shape[1])
             else:
                 be.copy_into(dst, src)
         self.model.optimizer.upload_hyper(self.hyper)

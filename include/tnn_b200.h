@@ -317,8 +317,13 @@ int tnn_colsum(int dtype, void* out, const void* g, int64_t R, int64_t C);
  * Backward: dz = gscale * (exp(z-M)/S - (1/m) y*exp(z-M)/(S q_i)), gscale read from g_dev[0]. */
 int tnn_ce_stats(int dtype, const void* z, int64_t B, int64_t C, void* stats_dev);
 int tnn_ce_merge_stats(int dtype, void* stats_out_dev, const void* stats_all_dev, int n_ranks);
+/* labels_dev (optional, tnn_ce_loss and tnn_ce_bwd): the targets as B int32 class indices instead of
+ * the dense one-hot rows y (then y may be NULL): q_i = p_{i,label_i}, the one non-zero term of the sum
+ * over the one-hot row -- bit-identical results without reading B x C labels (run.py:27-28 builds
+ * the dense rows with get_one_hot; utils/data_iterator.PrefetchIterator ships the indices). */
 int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-                const void* stats_dev, double m_global, void* q_dev, void* loss_dev);
+                const void* stats_dev, double m_global, void* q_dev, void* loss_dev,
+                const int32_t* labels_dev);
 /* stages 1 + 2 in ONE single-CTA launch for small logits (B <= 2048, B*C <= 16384: the
  * examples/mnist 128 x 10 case), single process only; same arithmetic and order as the staged path */
 int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
@@ -326,7 +331,8 @@ int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                const void* stats_dev, const void* q_dev, double m_global, const void* g_dev,
                void* stat_meta /* optional, float32: a zeroed f16 operand record (tnn_f16_meta_reset)
-                                  that receives max|dz| for the next tnn_split_f16 */);
+                                  that receives max|dz| for the next tnn_split_f16 */,
+               const int32_t* labels_dev);
 
 /* Small-MLP tail in ONE launch (examples/mnist/run.py:59-84 at batch 128: layers 2..L of the
  * 784-200-100-70-30-10 network).  Phase 1, 4 batch rows per CTA with the tail's weights resident in

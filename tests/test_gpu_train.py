@@ -427,6 +427,87 @@ def test_prefetch_iterator_integer_labels_become_one_hot_on_device():
         next(iter(PrefetchIterator(batch_size=8, num_classes=3)(x, np.eye(3)[lab % 3])))
 
 
+def test_cross_entropy_takes_class_indices_bit_identically():
+    """A one-hot target matrix that exists only as int32 class indices (be.LazyOneHot, what
+    PrefetchIterator(num_classes=C) yields): the fused cross-entropy reads the indices
+    (tnn_ce_loss / tnn_ce_bwd `labels_dev`) and its loss and dz are bit-identical to the dense-row
+    path (losses.py:24-32 on np.eye(C)[labels], run.py:27-28); the dense rows are never written
+    unless somebody asks for them; labels outside [0, C) behave like an all-zero row"""
+    import core._backend as be
+    from core.losses import SoftmaxCrossEntropyLoss
+    from core.tensor import Tensor
+    rng = np.random.RandomState(5)
+    for B, C, bad in ((300, 7, False), (4096, 10, False), (64, 4096, False), (513, 1001, False), (40, 12, True),
+                       (3000, 12, True)):
+        z = (rng.randn(B, C) * 3).astype(np.float32)
+        lab = rng.randint(0, C, B).astype(np.int32)
+        if bad:
+            lab[3], lab[17] = -1, C + 2
+        dense = np.zeros((B, C), np.float32)
+        ok = (lab >= 0) & (lab < C)
+        dense[np.arange(B)[ok], lab[ok]] = 1.0
+        out = []
+        for mode in ("dense", "lazy"):
+            zt = Tensor(z, requires_grad=True)
+            if mode == "dense":
+                yt = Tensor(dense)
+            else:
+                dl = be.from_numpy(lab.view(np.float32))
+                lazy = be.LazyOneHot(dl, C, be.empty((B, C), be.F32))
+                yt = Tensor(lazy)
+            zt.zero_grad()
+            loss = SoftmaxCrossEntropyLoss().loss(zt, yt)
+            loss.backward()
+            if mode == "lazy" and not be.ce_small_ok(B, C):
+                assert lazy._real is None          # the B x C rows were never written
+            out.append((np.array(loss.values), zt.grad.copy()))
+        if bad:
+            # -log(0) rows: inf loss on both paths, identical NaN/inf pattern
+            assert np.array_equal(out[0][0], out[1][0], equal_nan=True)
+            assert np.array_equal(out[0][1], out[1][1], equal_nan=True)
+            continue
+        assert np.array_equal(out[0][0], out[1][0])
+        assert np.array_equal(out[0][1], out[1][1])
+        # and both equal the oracle on the dense rows
+        rz = R.RefTensor(z.astype(np.float64), requires_grad=True)
+        rz.zero_grad()
+        rl = R.softmax_cross_entropy(rz, dense.astype(np.float64))
+        rl.backward()
+        assert abs(float(out[1][0]) - float(rl.values)) <= 1e-5 * max(1.0, abs(float(rl.values)))
+        assert np.max(np.abs(out[1][1] - rz.grad)) <= 1e-5 * np.max(np.abs(rz.grad))
+        # the rows appear on demand and are exactly np.eye(C)[labels]
+        assert np.array_equal(yt.values, dense)
+
+
+def test_training_on_index_labels_equals_training_on_dense_rows():
+    """three steps of an MLP fed by PrefetchIterator(num_classes=C) (class indices into the fused
+    loss) and by PrefetchIterator on the dense one-hot matrix: identical losses and parameters"""
+    from core.tensor import Tensor
+    from utils.data_iterator import PrefetchIterator
+    rng = np.random.RandomState(2)
+    n, D, C = 384, 40, 130
+    x = rng.rand(n, D).astype(np.float32)
+    lab = rng.randint(0, C, n)
+    dense = np.eye(C, dtype=np.float32)[lab]
+    res = []
+    for mode in ("dense", "index"):
+        np.random.seed(4)
+        net, model, loss_fn = _build([64, C])
+        it = (PrefetchIterator(batch_size=128)(x, dense) if mode == "dense"
+              else PrefetchIterator(batch_size=128, num_classes=C)(x, lab))
+        losses = []
+        for batch in it:
+            model.zero_grad()
+            loss = loss_fn.loss(model.forward(batch.inputs), batch.targets)
+            loss.backward()
+            model.step()
+            losses.append(float(loss.values))
+        res.append((losses, [p.values.copy() for layer in net.get_parameters() for p in layer.values()]))
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, b)
+
+
 def test_one_hot_kernel_edge_cases():
     """tnn_one_hot: float32 / float64 outputs, labels outside [0, C) give all-zero rows"""
     import core._backend as be

@@ -288,6 +288,23 @@ ce_rows_vec_kernel(const float* z, const float* y, int64_t B, int64_t C, const f
   }
 }
 
+// labels given as class indices (a one-hot y that was never materialised: utils/data_iterator.py ships
+// int32 labels and core/_backend.LazyOneHot names the dense rows): q_i = p_{i, label_i} -- the one
+// non-zero term of the sums above, so bit-identical to them -- without reading B x C labels
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_rows_label_kernel(const T* z, const int32_t* labels, int64_t B, int64_t C, const T* stats, T* q, T* nll) {
+  const T mx = stats[0], S = stats[1];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += stride) {
+    const int64_t l = labels[r];
+    T acc = T(0);
+    if (l >= 0 && l < C) acc += (m_exp(z[r * C + l] - mx) / S) * T(1);
+    q[r] = acc;
+    nll[r] = -m_log(acc);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_fold_loss_kernel(const T* nll, int64_t B, T m, T* loss) {
@@ -390,7 +407,7 @@ ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats
 template <typename T, typename TY, bool VEC>
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats, const T* q,
-              T m, const T* gptr, unsigned int* absmax_out) {
+              T m, const T* gptr, unsigned int* absmax_out, const int32_t* labels) {
   // rows over blockIdx.y, column slots over blockIdx.x * 256 + threadIdx.x: no per-element division.
   // VEC: a slot is 4 consecutive columns moved with 128-bit (z, dz) / 128- or 256-bit (y) accesses.
   constexpr int W = VEC ? 4 : 1;
@@ -400,14 +417,18 @@ ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* sta
   for (int64_t r = blockIdx.y; r < B; r += gridDim.y) {
     const T qm = q[r] * m;
     const T* zr = z + r * C;
-    const TY* yr = y + r * C;
+    const TY* yr = y + r * C;          // (not dereferenced when labels are given)
+    const int64_t lab = labels ? (int64_t)labels[r] : -1;
     T* dr = dz + r * C;
     for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < nslot; c += (int64_t)gridDim.x * 256) {
       T zv[W], yv[W], out[W];
       if constexpr (VEC) {
         const float4 t = *reinterpret_cast<const float4*>(zr + c * 4);
         zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
-        if constexpr (sizeof(TY) == 4) {
+        if (labels) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) yv[k] = (c * 4 + k == lab) ? T(1) : T(0);
+        } else if constexpr (sizeof(TY) == 4) {
           const float4 u = *reinterpret_cast<const float4*>(yr + c * 4);
           yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
         } else {
@@ -417,7 +438,7 @@ ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* sta
         }
       } else {
         zv[0] = zr[c];
-        yv[0] = (T)yr[c];
+        yv[0] = labels ? ((c == lab) ? T(1) : T(0)) : (T)yr[c];
       }
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -616,11 +637,18 @@ static int ce_stats_impl(const T* z, int64_t B, int64_t C, T* stats) {
 
 template <typename T, typename TY>
 static int ce_loss_impl(const T* z, const TY* y, int64_t B, int64_t C, const T* stats, double m,
-                        T* q, T* loss) {
+                        T* q, T* loss, const int32_t* labels) {
   cudaStream_t st = ctx().stream;
   void* scratch;
   if (get_scratch((size_t)B * sizeof(T), &scratch)) return 1;
   T* nll = (T*)scratch;
+  if (labels) {
+    ce_rows_label_kernel<T><<<ew_grid(B, 256), 256, 0, st>>>(z, labels, B, C, stats, q, nll);
+    TNN_POST_LAUNCH();
+    ce_fold_loss_kernel<T><<<1, 256, 0, st>>>(nll, B, (T)m, loss);
+    TNN_POST_LAUNCH();
+    return 0;
+  }
   int grid = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)ctx().sm_count * 8);
   bool vec = false;
   if constexpr (sizeof(T) == 4 && sizeof(TY) == 4)
@@ -640,19 +668,19 @@ static int ce_loss_impl(const T* z, const TY* y, int64_t B, int64_t C, const T* 
 
 template <typename T, typename TY>
 static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* stats,
-                       const T* q, double m, const T* g, unsigned int* absmax_out) {
+                       const T* q, double m, const T* g, unsigned int* absmax_out, const int32_t* labels) {
   cudaStream_t st = ctx().stream;
   // the 128-bit path is float32 logits with 4-column-aligned rows
-  const bool vec = sizeof(T) == 4 && (C % 4 == 0) && al16(dz) && al16(z) && al16(y);
+  const bool vec = sizeof(T) == 4 && (C % 4 == 0) && al16(dz) && al16(z) && (labels || al16(y));
   const int64_t nslot = vec ? C / 4 : C;
   int gx = (int)std::min<int64_t>(ceil_div(nslot, 256), 64);
   int64_t gy = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)ctx().sm_count * 8 / gx));
   if (gy > 65535) gy = 65535;
   if (vec) {
     if constexpr (sizeof(T) == 4)
-      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out);
+      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels);
   } else {
-    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out);
+    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels);
   }
   TNN_POST_LAUNCH();
   return 0;
@@ -699,17 +727,20 @@ int tnn_ce_merge_stats(int dtype, void* stats_out_dev, const void* stats_all_dev
 }
 
 int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-                const void* stats_dev, double m_global, void* q_dev, void* loss_dev) {
+                const void* stats_dev, double m_global, void* q_dev, void* loss_dev,
+                const int32_t* labels_dev) {
   TNN_REQUIRE_INIT();
   if (B <= 0 || C <= 0) TNN_FAIL("tnn_ce_loss: empty logits");
+  if (!y && !labels_dev) TNN_FAIL("tnn_ce_loss: neither dense labels nor class indices");
+  const int32_t* lab = labels_dev;
   if (dtype == TNN_F32 && y_dtype == TNN_F32)
-    return ce_loss_impl<float, float>((const float*)z, (const float*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev);
+    return ce_loss_impl<float, float>((const float*)z, (const float*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev, lab);
   if (dtype == TNN_F32 && y_dtype == TNN_F64)
-    return ce_loss_impl<float, double>((const float*)z, (const double*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev);
+    return ce_loss_impl<float, double>((const float*)z, (const double*)y, B, C, (const float*)stats_dev, m_global, (float*)q_dev, (float*)loss_dev, lab);
   if (dtype == TNN_F64 && y_dtype == TNN_F64)
-    return ce_loss_impl<double, double>((const double*)z, (const double*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev);
+    return ce_loss_impl<double, double>((const double*)z, (const double*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev, lab);
   if (dtype == TNN_F64 && y_dtype == TNN_F32)
-    return ce_loss_impl<double, float>((const double*)z, (const float*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev);
+    return ce_loss_impl<double, float>((const double*)z, (const float*)y, B, C, (const double*)stats_dev, m_global, (double*)q_dev, (double*)loss_dev, lab);
   TNN_FAIL("tnn_ce_loss: bad dtype");
 }
 
@@ -735,19 +766,21 @@ int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64
 
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                const void* stats_dev, const void* q_dev, double m_global, const void* g_dev,
-               void* stat_meta) {
+               void* stat_meta, const int32_t* labels_dev) {
   TNN_REQUIRE_INIT();
   if (B <= 0 || C <= 0) return 0;
+  if (!y && !labels_dev) TNN_FAIL("tnn_ce_bwd: neither dense labels nor class indices");
+  const int32_t* lab = labels_dev;
   unsigned int* am = (unsigned int*)stat_meta;   // word 0 of an f16 operand record (gemm_f16.cu)
   if (am && dtype != TNN_F32) TNN_FAIL("tnn_ce_bwd: operand statistics are float32 only");
   if (dtype == TNN_F32 && y_dtype == TNN_F32)
-    return ce_bwd_impl<float, float>((float*)dz, (const float*)z, (const float*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am);
+    return ce_bwd_impl<float, float>((float*)dz, (const float*)z, (const float*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am, lab);
   if (dtype == TNN_F32 && y_dtype == TNN_F64)
-    return ce_bwd_impl<float, double>((float*)dz, (const float*)z, (const double*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am);
+    return ce_bwd_impl<float, double>((float*)dz, (const float*)z, (const double*)y, B, C, (const float*)stats_dev, (const float*)q_dev, m_global, (const float*)g_dev, am, lab);
   if (dtype == TNN_F64 && y_dtype == TNN_F64)
-    return ce_bwd_impl<double, double>((double*)dz, (const double*)z, (const double*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am);
+    return ce_bwd_impl<double, double>((double*)dz, (const double*)z, (const double*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am, lab);
   if (dtype == TNN_F64 && y_dtype == TNN_F32)
-    return ce_bwd_impl<double, float>((double*)dz, (const double*)z, (const float*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am);
+    return ce_bwd_impl<double, float>((double*)dz, (const double*)z, (const float*)y, B, C, (const double*)stats_dev, (const double*)q_dev, m_global, (const double*)g_dev, am, lab);
   TNN_FAIL("tnn_ce_bwd: bad dtype");
 }
 

@@ -159,8 +159,9 @@ class PrefetchIterator(BaseIterator):
             if self.num_classes is not None:
                 n = xv.shape[0]
                 oh = buf["onehot"][step % 2].view((n, self.num_classes))
-                be.one_hot_into(oh, yv.ptr, n, self.num_classes)      # compute stream, after the copy
-                yv = oh
+                # the dense rows are only written if somebody asks for them: the fused cross-entropy
+                # takes the class indices (be.LazyOneHot)
+                yv = be.LazyOneHot(yv, self.num_classes, oh)
             yield Batch(inputs=Tensor(xv), targets=Tensor(yv))
             if last:
                 return
