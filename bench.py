@@ -295,10 +295,14 @@ def one_hot_host(labels, C):
 class Stepper(object):
     """the reference's five-line training loop body (run.py:79-83), or its recorded replay"""
 
-    def __init__(self, cfg, use_graph):
+    def __init__(self, cfg, use_graph, defer_loop=False):
+        """use_graph: Model.train_step instead of the five lines.  defer_loop: leave the engine's
+        transparent recording of the five-line loop on (core/_deferred.py: small steps only); off,
+        the five lines are launched kernel by kernel as written."""
         from core.losses import SoftmaxCrossEntropyLoss
         np.random.seed(0)
         self.net, self.model = build_model(cfg)
+        self.model.defer_loop = bool(defer_loop)
         self.loss_layer = SoftmaxCrossEntropyLoss()
         self.use_graph = use_graph
 
@@ -438,8 +442,13 @@ def measure_mnist(steps=2000, warmup=50):
     x_dev = [be.from_numpy(x) for x in xs]
     y_dev = [be.from_numpy(one_hot_host(y, C)) for y in ys]
     out = {"config": "BASELINE.json configs[0]", "workload": cfg["name"], "batch": B}
-    for mode, use_graph in (("eager_five_line_loop", False), ("recorded_train_step", True)):
-        stepper = Stepper(cfg, use_graph)
+    # eager: the five lines of run.py:79-83 launched kernel by kernel; five_line_loop: the same five
+    # lines, unmodified, with the engine's transparent recording on (its default); train_step: the
+    # explicit one-call API
+    for mode, use_graph, defer in (("eager_five_line_loop", False, False),
+                                   ("five_line_loop_recorded_transparently", False, True),
+                                   ("recorded_train_step", True, False)):
+        stepper = Stepper(cfg, use_graph, defer)
         ms, launches, _, _, last = timed_steps(stepper, x_dev, y_dev, steps, warmup, profile_gemm=False)
         out[mode] = {"ms_per_step": ms / steps, "value": B * steps / (ms * 1e-3), "unit": "samples/s",
                      "steps": steps, "launches_per_step": launches / steps, "final_loss": last}

@@ -132,7 +132,7 @@ _SIGNATURES = {
     "tnn_one_hot": [_c_int, _c_vp, _c_vp, _c_i64, _c_i64],
     "tnn_mlp_tail_workspace": [_c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp],
     "tnn_mlp_tail_step": [_c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_int,
-                          _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+                          _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "tnn_opt_step": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int],
     "tnn_opt_step_dev": [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "tnn_nccl_unique_id": [_c_vp],
@@ -1252,6 +1252,9 @@ class MLPTail(object):
         self.stats = zeros((2 * self.n_ctas,), F32)
         self.loss_part = zeros((self.n_ctas,), F32)
         self.counters = zeros((16,), F32)             # uint32 rendezvous counters, rearmed by the kernel
+        self.logits = empty((batch, dims[-1]), F32)   # the network's output rows of the last pass
+        # dL/dlogits of the last pass: the last layer's dL/dz rows in the phase-1 -> phase-2 scratch
+        self.dlogits = self.scratch.view((batch, dims[-1]), scratch.value - batch * dims[-1])
 
     @classmethod
     def eligible(cls, dims, batch):
@@ -1276,7 +1279,7 @@ class MLPTail(object):
         if _lib.tnn_mlp_tail_step(self.L, self.in_dims, self.out_dims, wp, bp, go, grad_base.ptr, n_grad,
                                   z1.ptr, y.ptr, _DT_CODE[y.dtype], self.batch, float(m_global), dz1.ptr,
                                   loss_out.ptr, self.scratch.ptr, self.stats.ptr, self.loss_part.ptr,
-                                  self.counters.ptr):
+                                  self.counters.ptr, self.logits.ptr):
             _raise("tnn_mlp_tail_step")
 
 

@@ -15,7 +15,7 @@ batch.
 import numpy as np
 
 import core.ops as ops
-from core.tensor import as_tensor
+from core.tensor import Tensor, as_tensor
 
 
 class BaseLoss(object):
@@ -33,6 +33,13 @@ class SoftmaxCrossEntropyLoss(BaseLoss):
         self._weight = None if weight is None else np.asarray(weight)
 
     def loss(self, logits, labels):
+        if type(logits) is not Tensor and isinstance(logits, Tensor):
+            # a prediction Model.forward postponed (core/_deferred.py): the loss is postponed with it
+            import core._deferred as deferred
+            if type(logits) is deferred.LazyTensor:
+                lazy = deferred.defer_loss(self, logits, labels)
+                if lazy is not None:
+                    return lazy
         if self._weight is not None:
             raise NotImplementedError(
                 "class weights are not supported (the reference's weighted path is broken, "

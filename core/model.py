@@ -13,7 +13,9 @@ import pickle
 import numpy as np
 
 import core._backend as be
+import core._deferred as deferred
 import core._dist as dist
+import core.tensor as T
 
 _ALIGN = 64  # elements; keeps every parameter slot 256-byte aligned for 128-bit kernels / TMA
 
@@ -23,6 +25,16 @@ class Model(object):
     # train_step on a small Dense/ReLU MLP with SoftmaxCrossEntropyLoss (the examples/mnist network)
     # records the fused small-MLP pass (csrc/mlp_fused.cu) instead of the layer-by-layer step
     fuse_small_mlp = True
+    # the five-line loop of run.py:78-83 reaches the recorded step on its own (core/_deferred.py)
+    defer_loop = deferred.ENABLED
+    # ... for launch-bound steps only: batch (inputs + targets) and parameter counts up to these many
+    # elements.  A wide step gains nothing from a replay (measured: 7.91 vs 7.92 ms for the 4 x 4096
+    # MLP) and its recording would pin the step's temporaries.
+    # the loop's recording is the layer-by-layer one (bit-identical to the eager lines); True lets it
+    # be the fused small-MLP pass where that applies (rounding-level differences, see train_step)
+    defer_loop_may_fuse = False
+    defer_loop_max_batch_elems = 1 << 22
+    defer_loop_max_param_elems = 1 << 23
 
     def __init__(self, net, loss, optimizer):
         self.net = net
@@ -31,9 +43,46 @@ class Model(object):
         self._phase = "TRAIN"
         self._arena = None  # dict(params=[...], p=DArray, g=DArray, slots=[(off, size)])
         self._captured = {}  # batch signature -> "warm" | _CapturedStep | "eager"
+        self._out_sig = {}   # (input shape, dtype) -> (output shape, dtype) seen in TRAIN phase
+        self._noloop = set() # input signatures whose iteration could not be recorded
+        self._stash_pred = False
+        self._last_pred = None
 
     def forward(self, inputs):
+        if self.defer_loop and self._phase == "TRAIN" and type(inputs) is T.Tensor:
+            sig = self._out_sig.get((inputs.shape, inputs.dtype.str))
+            if sig is not None and self._loop_can_defer(inputs):
+                return deferred.begin(self, inputs, sig[0], sig[1])
+            out = self.net.forward(inputs)
+            self._note_output(inputs, out)
+            return out
         return self.net.forward(inputs)
+
+    def _note_output(self, inputs, out):
+        if type(out) is T.Tensor and out.requires_grad:
+            self._out_sig[(inputs.shape, inputs.dtype.str)] = (out.shape, out.dtype)
+
+    def _loop_can_defer(self, x):
+        """is this forward() the second line of a run.py-style iteration that step() could replay?
+        Parameters in their arena with freshly zeroed gradients (zero_grad() was the first line), a
+        built-in update rule, an input that needs no gradient, and no earlier failure to record
+        this batch shape."""
+        if x.requires_grad or (x.shape, x.dtype.str) in self._noloop:
+            return False
+        if x._data.size > self.defer_loop_max_batch_elems:
+            return False
+        opt = self.optimizer
+        if opt.opt_code is None or not opt.uses_builtin_rule():
+            return False
+        plist = self._param_list()
+        if not plist or not self._arena_valid(plist):
+            return False
+        if self._arena["p"].size > self.defer_loop_max_param_elems:
+            return False
+        for p in plist:
+            if not (p._grad_zero and p._grad is p._gslot and p.requires_grad):
+                return False
+        return True
 
     def predict(self, inputs):
         """forward pass without an autograd graph (the evaluation at run.py:87-91): activations are
@@ -145,6 +194,12 @@ class Model(object):
 
     # ------------------------------------------------------------------ training step
     def step(self):
+        chain = T._DEFERRED[0]
+        if chain is not None:
+            T._DEFERRED[0] = None
+            if chain.model is self and chain.stage == "backward" and self._deferred_step(chain):
+                return
+            chain.materialise()
         plist = self._param_list()
         # the fused arena kernel implements the built-in update rules only: an optimiser whose class
         # overrides the reference's extension points (_compute_step / compute_step) goes through
@@ -179,6 +234,49 @@ class Model(object):
                 p._drop_grad()  # reference: `param += step` leaves grad = None (tensor.py:35-38)
             return
         self._step_generic()
+
+    def _deferred_step(self, chain):
+        """zero_grad / forward / loss / backward were postponed (core/_deferred.py) and this is the
+        iteration's step(): replay the recording of this batch shape if there is one (made once the
+        shape has been through one eager iteration).  False = run the postponed lines eagerly."""
+        x, y, loss_obj = chain.x, chain.y, chain.loss_obj
+        # the layer-by-layer recording: the same kernels in the same order as the eager lines, so
+        # the loop's numbers do not depend on whether an iteration was replayed (the fused
+        # small-MLP pass sums in another order and stays behind the explicit train_step)
+        key = self._step_key(x, y, loss_obj, "loop-fused" if self.defer_loop_may_fuse else "loop")
+        state = self._captured.get(key)
+        if state is not None and not isinstance(state, str) and not self._arena_valid(self._param_list()):
+            self._drop_recordings()
+            state = None
+        if state is None:
+            # first sight of this shape: it runs as written; the next one is recorded
+            self._captured[key] = "warm"
+            return False
+        if state == "eager":
+            self._noloop.add((x.shape, x.dtype.str))
+            return False
+        if state == "warm":
+            state = self._capture_step(x, y, key, loss_obj, allow_fused=self.defer_loop_may_fuse)
+            if state is None:
+                self._captured[key] = "eager"
+                self._noloop.add((x.shape, x.dtype.str))
+                return False
+            self._captured[key] = state
+        deferred.pin_live_prediction(state)
+        loss = state.run(x, y)
+        deferred.serve_after_replay(chain, state, loss._data)
+        return True
+
+    def _drop_recordings(self):
+        for st in self._captured.values():
+            if not isinstance(st, str):
+                st.destroy()
+        self._captured = {}
+
+    def _step_key(self, x, y, loss_obj, kind="train_step"):
+        # (loss objects of one class without state are interchangeable: run.py:72-73 builds two)
+        return (kind, x.shape, x.dtype.str, y.shape, y.dtype.str, dist.world_size(), id(self.optimizer),
+                type(loss_obj), id(getattr(loss_obj, "_weight", None)), self._phase)
 
     def _step_generic(self):
         """the reference's three stages verbatim (model.py:45-61), on device arrays"""
@@ -219,19 +317,16 @@ class Model(object):
         eager step (tests/test_gpu_graph.py).  A replay does not refresh the per-layer `inputs`
         bookkeeping or non-leaf `.grad`s -- use the five lines above when those are wanted."""
         from core.tensor import Tensor
+        T._flush_deferred()
         x = inputs if isinstance(inputs, Tensor) else Tensor(inputs)
         y = targets if isinstance(targets, Tensor) else Tensor(targets)
-        key = (x.shape, x.dtype.str, y.shape, y.dtype.str, dist.world_size(), id(self.optimizer),
-               id(self.loss), self._phase)
+        key = self._step_key(x, y, self.loss)
         state = self._captured.get(key)
         if state is not None and not isinstance(state, str):
             # a recorded step names the parameter arenas: if a parameter was rebound since
             # (p.values = ..., load(), set_parameters) every recording is stale
             if not self._arena_valid(self._param_list()):
-                for st in self._captured.values():
-                    if not isinstance(st, str):
-                        st.destroy()
-                self._captured = {}
+                self._drop_recordings()
                 state = None
         if state is None or state == "eager":
             loss = self._eager_step(x, y)
@@ -245,26 +340,40 @@ class Model(object):
                 self._captured[key] = "eager"
                 return self._eager_step(x, y)
             self._captured[key] = state
+        deferred.pin_live_prediction(state)
         return state.run(x, y)
 
-    def _eager_step(self, x, y):
+    def _eager_step(self, x, y, loss_obj=None):
         self.zero_grad()
-        pred = self.forward(x)
-        loss = self.loss.loss(pred, y)
+        pred = self.net.forward(x)
+        if self._stash_pred:             # a recording keeps its prediction's buffers (core/_deferred.py)
+            self._last_pred = pred
+        loss = (loss_obj or self.loss).loss(pred, y)
         loss.backward()
         self.step()
         return loss
 
-    def _capture_step(self, x, y, key):
+    def _capture_step(self, x, y, key, loss_obj=None, allow_fused=True):
+        loss_obj = loss_obj or self.loss
         plist = self._param_list()
         if not (plist and self._arena_valid(plist)) or self.optimizer.opt_code is None:
             return None
         if not self.optimizer.uses_builtin_rule():
             return None
-        plan = self._fused_mlp_plan(x, y) if self.fuse_small_mlp else None
-        body = None if plan is None else (lambda xt, yt: self._fused_mlp_step(xt, yt, plan))
+        plan = self._fused_mlp_plan(x, y, loss_obj) if (self.fuse_small_mlp and allow_fused) else None
+        if plan is not None:
+            body = lambda xt, yt: self._fused_mlp_step(xt, yt, plan)
+        else:
+            body = lambda xt, yt: self._eager_step(xt, yt, loss_obj)
+        self._stash_pred = plan is None
         try:
             step = _CapturedStep(self, x, y, body, keepalive=plan)
+            if plan is not None:
+                tail = plan["tail"]
+                step.prediction_source = lambda: (tail.logits, tail.dlogits)
+            else:
+                pred = self._last_pred
+                step.prediction_source = lambda: (pred._data, pred._grad)
         except be.BackendError:
             # something in the step cannot be recorded (a host read of a device value, an upload,
             # scratch growth): the aborted recording ran nothing, so drop what it cached and let the
@@ -274,22 +383,25 @@ class Model(object):
                 p._touch()
             self.zero_grad()
             return None
+        finally:
+            self._stash_pred, self._last_pred = False, None
         if not self._arena_valid(plist):   # the recorded step left the fused path
             step.destroy()
             return None
         return step
 
     # ------------------------------------------------------------------ fused small-MLP step
-    def _fused_mlp_plan(self, x, y):
+    def _fused_mlp_plan(self, x, y, loss_obj=None):
         """Is this (network, loss, batch) the pattern csrc/mlp_fused.cu handles?  A Dense/ReLU stack
         of float32 layers (run.py:59-69) whose layers after the first fit one SM's shared memory,
         the reference's SoftmaxCrossEntropyLoss, one process.  Returns the plan or None."""
         from core.layers import Dense, ReLU
         from core.losses import SoftmaxCrossEntropyLoss
         layers = self.net.layers
-        if dist.world_size() != 1 or type(self.loss) is not SoftmaxCrossEntropyLoss:
+        loss_obj = loss_obj or self.loss
+        if dist.world_size() != 1 or type(loss_obj) is not SoftmaxCrossEntropyLoss:
             return None
-        if getattr(self.loss, "_weight", None) is not None:
+        if getattr(loss_obj, "_weight", None) is not None:
             return None
         if len(layers) < 3 or len(layers) % 2 == 0:
             return None
@@ -343,6 +455,9 @@ class Model(object):
         return Tensor(loss)
 
     def zero_grad(self):
+        chain = T._DEFERRED[0]
+        if chain is not None and chain.stage == "backward":
+            T._flush_deferred()          # a postponed backward() has gradients to leave behind first
         be.new_split_epoch()
         plist = self._param_list()
         if plist and self._arena_valid(plist):
@@ -412,6 +527,7 @@ class _CapturedStep(object):
         self.graph.replay()
         for p in self.plist:
             p._touch()
+            p._drop_grad()   # as after the eager step(): `param += step` leaves grad = None (tensor.py:35-38)
         # the loss buffer is rewritten by the next replay: hand out a copy
         return Tensor(be.clone(self.loss))
 

@@ -23,6 +23,18 @@ import core.ops as ops
 _SCALAR_TYPES = (int, float, bool, np.integer, np.floating, np.bool_)
 
 
+# the postponed training iteration, if any (core/_deferred.py): anything that reads or changes a
+# gradient, or changes a tensor's storage, first runs it
+_DEFERRED = [None]
+
+
+def _flush_deferred():
+    chain = _DEFERRED[0]
+    if chain is not None:
+        _DEFERRED[0] = None
+        chain.materialise()
+
+
 def _readonly(arr):
     arr.setflags(write=False)
     return arr
@@ -59,7 +71,7 @@ class Tensor(object):
         self._fused_bwd = None   # optional: all input gradients of this node from one launch (ops._dense_node)
         self.requires_grad = requires_grad
         if self.requires_grad:
-            self.zero_grad()
+            self._grad_zero = True   # zero_grad() of a tensor that has no arena slot yet
         self.dependency = dependency if dependency is not None else []
 
     # ------------------------------------------------------------------ storage
@@ -73,6 +85,8 @@ class Tensor(object):
     @values.setter
     def values(self, new_values):
         # tensor.py:35-38: replaces the storage and drops the gradient
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         if isinstance(new_values, be.DArray):
             self._data = new_values
         elif isinstance(new_values, Tensor):
@@ -102,6 +116,8 @@ class Tensor(object):
     @property
     def grad(self):
         """host copy of the accumulated gradient, or None (tensor.py:22)"""
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         if self._grad_zero:      # zeroed and nothing accumulated since (an arena slot is not
             if self._grad_host is None:   # cleared until something is written or the step needs it)
                 self._grad_host = _readonly(np.zeros(self.shape, dtype=self._data.dtype))
@@ -114,6 +130,8 @@ class Tensor(object):
 
     @grad.setter
     def grad(self, value):
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         self._grad_host = None
         if value is None:
             self._grad = None
@@ -211,6 +229,8 @@ class Tensor(object):
 
     # ------------------------------------------------------------------ in-place: rebind, not recorded
     def _rebind(self, data):
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         self._data = data
         self._host = None
         self._drop_grad()
@@ -266,6 +286,8 @@ class Tensor(object):
     # ------------------------------------------------------------------ autograd
     def zero_grad(self):
         """tensor.py:170-171.  Lazy: nothing is allocated until a gradient arrives."""
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         self._grad_host = None
         if self._gslot is not None:
             # the slot is not cleared here: the first gradient overwrites it, and Model.step clears
@@ -335,6 +357,8 @@ class Tensor(object):
 
     def backward(self, grad=None):
         assert self.requires_grad, "Call backward() on a non-requires-grad tensor."
+        if _DEFERRED[0] is not None:
+            _flush_deferred()
         if grad is None:
             if self._data.shape == ():
                 seed = be.ones_scalar(self._data.dtype)      # shared constant, no launch

@@ -355,7 +355,9 @@ int tnn_mlp_tail_workspace(int n_layers, const int64_t* in_dims, const int64_t* 
 int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_dims, const void* const* w,
                       const void* const* b, const int64_t* grad_off, void* grad, int64_t n_grad,
                       const void* z1, const void* y, int y_dtype, int64_t B, double m_global, void* dz1,
-                      void* loss_out, void* scratch, void* stats, void* loss_part, void* counters);
+                      void* loss_out, void* scratch, void* stats, void* loss_part, void* counters,
+                      void* logits_out /* optional [B,out[L-1]] float32: the network's output rows
+                                          (model.py:27-28 forward's return value) */);
 
 /* fused optimizer step on flat buffers (optimizer.py:12-35 flatten + _compute_step + model.py:59-61
  * param += step).  s0/s1 are the optimizer state vectors (Adam m,v; RMSProp ms,mom; ...), h[] the

@@ -153,7 +153,7 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
                 const TY* __restrict__ y, float m_global, float* __restrict__ grad,
                 float* __restrict__ gscratch, float* __restrict__ dz1_out, float2* __restrict__ stats,
                 float* __restrict__ loss_part, float* __restrict__ loss_out,
-                unsigned int* __restrict__ counters) {
+                unsigned int* __restrict__ counters, float* __restrict__ logits_out) {
   extern __shared__ float4 smem4[];
   float* sm = reinterpret_cast<float*>(smem4);
   __shared__ float red[THREADS / 32];
@@ -242,6 +242,13 @@ mlp_tail_kernel(const __grid_constant__ TailArgs a, const float* __restrict__ z1
     {
       const float4 z = has_col ? reinterpret_cast<const float4*>(sm + a.z_s[L])[tid] : f4(0.f);
       zv[0] = z.x; zv[1] = z.y; zv[2] = z.z; zv[3] = z.w;
+    }
+    if (logits_out != nullptr && has_col) {
+      // the network's output rows (Model.forward's return value), for a caller that reads them
+      // after the step
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (row0 + r < B) logits_out[(int64_t)(row0 + r) * C + tid] = zv[r];
     }
     float lmax = -INFINITY;
 #pragma unroll
@@ -480,7 +487,8 @@ int tnn_mlp_tail_workspace(int n_layers, const int64_t* in_dims, const int64_t* 
 int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_dims, const void* const* w,
                       const void* const* b, const int64_t* grad_off, void* grad, int64_t n_grad,
                       const void* z1, const void* y, int y_dtype, int64_t B, double m_global, void* dz1,
-                      void* loss_out, void* scratch, void* stats, void* loss_part, void* counters) {
+                      void* loss_out, void* scratch, void* stats, void* loss_part, void* counters,
+                      void* logits_out) {
   TNN_REQUIRE_INIT();
   int64_t smem_bytes = 0, n_ctas = 0, scratch_floats = 0;
   if (tnn_mlp_tail_workspace(n_layers, in_dims, out_dims, B, &smem_bytes, &n_ctas, &scratch_floats)) return 1;
@@ -553,7 +561,7 @@ int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_d
     }
     TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, a, (const float*)z1, (int)B, (const float*)y, (float)m_global,
                                 (float*)grad, (float*)scratch, (float*)dz1, (float2*)stats, (float*)loss_part,
-                                (float*)loss_out, (unsigned int*)counters));
+                                (float*)loss_out, (unsigned int*)counters, (float*)logits_out));
   } else if (y_dtype == TNN_F64) {
     auto kern = mlp::mlp_tail_kernel<double>;
     if (!attr_set[1]) {
@@ -562,7 +570,7 @@ int tnn_mlp_tail_step(int n_layers, const int64_t* in_dims, const int64_t* out_d
     }
     TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, a, (const float*)z1, (int)B, (const double*)y, (float)m_global,
                                 (float*)grad, (float*)scratch, (float*)dz1, (float2*)stats, (float*)loss_part,
-                                (float*)loss_out, (unsigned int*)counters));
+                                (float*)loss_out, (unsigned int*)counters, (float*)logits_out));
   } else {
     TNN_FAIL("tnn_mlp_tail_step: labels must be float32 or float64");
   }
