@@ -102,6 +102,9 @@ class LazyTensor(Tensor):
             self._lz_chain.materialise()
         else:
             self._pin()
+        if type(self) is LazyTensor:     # the postponed lines raised earlier and never produced it
+            raise RuntimeError("this tensor belongs to a postponed training iteration whose lines "
+                               "raised when they were run; it has no values")
 
     @property
     def _data(self):

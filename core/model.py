@@ -33,6 +33,7 @@ class Model(object):
     # the loop's recording is the layer-by-layer one (bit-identical to the eager lines); True lets it
     # be the fused small-MLP pass where that applies (rounding-level differences, see train_step)
     defer_loop_may_fuse = False
+    defer_loop_max_recordings = 8     # distinct batch shapes a loop may have recorded at a time
     defer_loop_max_batch_elems = 1 << 22
     defer_loop_max_param_elems = 1 << 23
 
@@ -256,6 +257,13 @@ class Model(object):
             self._noloop.add((x.shape, x.dtype.str))
             return False
         if state == "warm":
+            n_rec = sum(1 for k, st in self._captured.items()
+                        if not isinstance(st, str) and k[0].startswith("loop"))
+            if n_rec >= self.defer_loop_max_recordings:
+                # a loop over ever-changing batch shapes: each recording pins its temporaries
+                self._captured[key] = "eager"
+                self._noloop.add((x.shape, x.dtype.str))
+                return False
             state = self._capture_step(x, y, key, loss_obj, allow_fused=self.defer_loop_may_fuse)
             if state is None:
                 self._captured[key] = "eager"

@@ -293,3 +293,20 @@ def test_batch_iterator_epochs_through_the_postponed_loop():
     assert res[False][0] == res[True][0]
     for pa, pb in zip(res[False][1], res[True][1]):
         assert np.array_equal(pa, pb)
+
+
+def test_recordings_are_capped_for_loops_over_many_shapes():
+    """every recording pins its temporaries: a loop whose batch shape keeps changing stops being
+    recorded after defer_loop_max_recordings shapes and runs as written -- same numbers either way"""
+    sizes = [b for b in (16, 24, 32, 40, 48) for _ in range(4)]
+    batches = _batches(40, 6, sizes, seed=3)
+    res = {}
+    for defer in (False, True):
+        net, model = _model([24, 6], 2, 40, defer=defer, fuse=False)
+        model.defer_loop_max_recordings = 3
+        res[defer] = ([float(v) for v in _loop(model, batches)], _params(net))
+        if defer:
+            assert len(_recordings(model)) == 3
+    assert res[False][0] == res[True][0]
+    for pa, pb in zip(res[False][1], res[True][1]):
+        assert np.array_equal(pa, pb)
