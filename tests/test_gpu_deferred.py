@@ -310,3 +310,37 @@ def test_recordings_are_capped_for_loops_over_many_shapes():
     assert res[False][0] == res[True][0]
     for pa, pb in zip(res[False][1], res[True][1]):
         assert np.array_equal(pa, pb)
+
+
+_PDL_SCRIPT = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(tests)r)
+import test_gpu_deferred as td
+net, model = td._model(td.MNIST, 3, 784, defer=True, fuse=False)
+losses = td._loop(model, td._batches(784, 10, [128] * 8))
+print("RESULT " + json.dumps([float(v).hex() for v in losses]
+                             + [float(np.sum(p.astype(np.float64))).hex() for p in td._params(net)]))
+"""
+
+
+def test_programmatic_dependent_launch_is_bit_identical():
+    """TNN_PDL=1 (experiment, profiles/r02h_pdl_experiment.md): the small kernels of the recorded step
+    are launched with the programmatic-dependency attribute and wait at their top for their
+    predecessor; same bits as the ordinary launches (the switch is read once per process, hence the
+    two child processes)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _PDL_SCRIPT % {"root": root, "tests": os.path.join(root, "tests")}
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, TNN_PDL=flag)
+        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+        out[flag] = json.loads(line[len("RESULT "):])
+    assert out["0"] == out["1"]

@@ -346,6 +346,7 @@ ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats
   __shared__ T zs[CE_SMALL_STAGE];
   const int64_t n = B * C;
   const bool first = threadIdx.x < 256;
+  pdl_sync();
   // one trip to global memory for the logits when they fit in shared memory: the max pass, the
   // sum-exp pass and the per-row pass then read the staged copy (three dependent round trips
   // were most of this kernel's 9 us)
@@ -411,6 +412,7 @@ ce_bwd_kernel(T* dz, const T* z, const TY* y, int64_t B, int64_t C, const T* sta
   // rows over blockIdx.y, column slots over blockIdx.x * 256 + threadIdx.x: no per-element division.
   // VEC: a slot is 4 consecutive columns moved with 128-bit (z, dz) / 128- or 256-bit (y) accesses.
   constexpr int W = VEC ? 4 : 1;
+  pdl_sync();
   const T mx = stats[0], S = stats[1], g = gptr[0];
   const int64_t nslot = C / W;
   unsigned int amax = 0u;   // bits of max |dz| (float32 only): the operand statistics of the next split
@@ -469,6 +471,7 @@ template <int OPT, typename T>
 __global__ void __launch_bounds__(256)
 opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH hh,
            const OptH* hdev) {
+  pdl_sync();
   if (hdev) hh = *hdev;   // captured step: the coefficients are refreshed in device memory per replay
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -532,6 +535,7 @@ opt_kernel(T* param, T* step_out, const T* grad, T* s0, T* s1, int64_t n, OptH h
 template <typename T>
 __global__ void __launch_bounds__(256)
 adam_vec_kernel(T* param, const T* grad, T* s0, T* s1, int64_t nv, OptH hh, const OptH* hdev) {
+  pdl_sync();
   if (hdev) hh = *hdev;
   using VT = typename V4<T>::type;
   using U = typename V4<T>::U;
@@ -566,38 +570,40 @@ static int opt_dispatch(int opt, T* param, T* step_out, const T* grad, T* s0, T*
                         const OptH& hh, const OptH* hdev) {
   cudaStream_t st = ctx().stream;
   int grid = ew_grid(n, 256);
+  // a small arena is the tail of a launch-bound chain (the MNIST-sized step): programmatic dependency
+  const bool pdl = grid <= 2 * ctx().sm_count;
   switch (opt) {
     case TNN_OPT_SGD:
-      opt_kernel<TNN_OPT_SGD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+      TNN_CUDA(launch_small(opt_kernel<TNN_OPT_SGD, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       break;
     case TNN_OPT_ADAM: {
       constexpr int W = V4<T>::W;
       if (param && !step_out && al16(param) && al16(grad) && al16(s0) && al16(s1) && n >= W) {
         int64_t nv = n / W;
-        adam_vec_kernel<T><<<ew_grid(nv, 256), 256, 0, st>>>(param, grad, s0, s1, nv, hh, hdev);
-        TNN_POST_LAUNCH();
+        TNN_CUDA(launch_small(adam_vec_kernel<T>, dim3(ew_grid(nv, 256)), dim3(256), st, pdl, 1u, param, grad, s0, s1, nv, hh, hdev));
+        ctx().launches++;
         int64_t done = nv * W;
         if (done < n)
-          opt_kernel<TNN_OPT_ADAM, T><<<1, 256, 0, st>>>(param + done, nullptr, grad + done,
-                                                         s0 + done, s1 + done, n - done, hh, hdev);
+          TNN_CUDA(launch_small(opt_kernel<TNN_OPT_ADAM, T>, dim3(1), dim3(256), st, pdl, 1u, param + done,
+                                (T*)nullptr, grad + done, s0 + done, s1 + done, n - done, hh, hdev));
         else
           return 0;
       } else {
-        opt_kernel<TNN_OPT_ADAM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+        TNN_CUDA(launch_small(opt_kernel<TNN_OPT_ADAM, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       }
       break;
     }
     case TNN_OPT_RMSPROP:
-      opt_kernel<TNN_OPT_RMSPROP, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+      TNN_CUDA(launch_small(opt_kernel<TNN_OPT_RMSPROP, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       break;
     case TNN_OPT_MOMENTUM:
-      opt_kernel<TNN_OPT_MOMENTUM, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+      TNN_CUDA(launch_small(opt_kernel<TNN_OPT_MOMENTUM, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       break;
     case TNN_OPT_ADAGRAD:
-      opt_kernel<TNN_OPT_ADAGRAD, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+      TNN_CUDA(launch_small(opt_kernel<TNN_OPT_ADAGRAD, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       break;
     case TNN_OPT_ADADELTA:
-      opt_kernel<TNN_OPT_ADADELTA, T><<<grid, 256, 0, st>>>(param, step_out, grad, s0, s1, n, hh, hdev);
+      TNN_CUDA(launch_small(opt_kernel<TNN_OPT_ADADELTA, T>, dim3(grid), dim3(256), st, pdl, 1u, param, step_out, grad, s0, s1, n, hh, hdev));
       break;
     default:
       TNN_FAIL("tnn_opt_step: unknown optimizer code");
@@ -676,13 +682,17 @@ static int ce_bwd_impl(T* dz, const T* z, const TY* y, int64_t B, int64_t C, con
   int gx = (int)std::min<int64_t>(ceil_div(nslot, 256), 64);
   int64_t gy = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)ctx().sm_count * 8 / gx));
   if (gy > 65535) gy = 65535;
+  // a small grid is part of a launch-bound chain (the MNIST-sized step): programmatic dependency
+  const bool pdl = (int64_t)gx * gy <= 2 * (int64_t)ctx().sm_count;
   if (vec) {
     if constexpr (sizeof(T) == 4)
-      ce_bwd_kernel<T, TY, true><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels);
+      TNN_CUDA(launch_small(ce_bwd_kernel<T, TY, true>, dim3(gx, (unsigned)gy), dim3(256), st, pdl, 1u,
+                            dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels));
   } else {
-    ce_bwd_kernel<T, TY, false><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels);
+    TNN_CUDA(launch_small(ce_bwd_kernel<T, TY, false>, dim3(gx, (unsigned)gy), dim3(256), st, pdl, 1u,
+                          dz, z, y, B, C, stats, q, (T)m, g, absmax_out, labels));
   }
-  TNN_POST_LAUNCH();
+  ctx().launches++;
   return 0;
 }
 
@@ -751,13 +761,13 @@ int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64
   if (B > CE_SMALL_MAX_ROWS || B * C > 16384) TNN_FAIL("tnn_ce_fwd_small: at most 2048 rows and 16384 logits");
   cudaStream_t st = ctx().stream;
   if (dtype == TNN_F32 && y_dtype == TNN_F32)
-    ce_fwd_small_kernel<float, float><<<1, 1024, 0, st>>>((const float*)z, (const float*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev);
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, float>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const float*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev));
   else if (dtype == TNN_F32 && y_dtype == TNN_F64)
-    ce_fwd_small_kernel<float, double><<<1, 1024, 0, st>>>((const float*)z, (const double*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev);
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, double>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const double*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev));
   else if (dtype == TNN_F64 && y_dtype == TNN_F64)
-    ce_fwd_small_kernel<double, double><<<1, 1024, 0, st>>>((const double*)z, (const double*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev);
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, double>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const double*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev));
   else if (dtype == TNN_F64 && y_dtype == TNN_F32)
-    ce_fwd_small_kernel<double, float><<<1, 1024, 0, st>>>((const double*)z, (const float*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev);
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, float>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const float*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev));
   else
     TNN_FAIL("tnn_ce_fwd_small: bad dtype");
   TNN_POST_LAUNCH();

@@ -214,6 +214,7 @@ gemm_simt_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ A, int64_
                  const T* __restrict__ mask_src, int64_t kslice) {
   __shared__ __align__(16) T As[BK][Pitch<BM, TM>::value];
   __shared__ __align__(16) T Bs[BK][Pitch<BN, TN>::value];
+  pdl_sync();
   gemm_tile<T, BM, BN, BK, TM, TN, SPLITK>(As, Bs, (int)blockIdx.x, (int)blockIdx.y, C, ldc, A, a_rs, a_cs,
                                            B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, kslice);
 }
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(256, 2)
 gemm_simt_group_kernel(const SimtGroup<T> grp) {
   __shared__ __align__(16) T As[BK][Pitch<32, 2>::value];
   __shared__ __align__(16) T Bs[BK][Pitch<32, 2>::value];
+  pdl_sync();
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < 3; ++i)
@@ -313,25 +315,19 @@ static int gemm_simt_impl(T* C, int64_t ldc, const T* A, int64_t a_rs, int64_t a
     if (S > 1 && grid.y <= 65535) {
       grid.z = (unsigned)S;
       const int64_t kslice = ceil_div(K, S);
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = 0;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 1;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = (unsigned)S;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      TNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_simt_kernel<T, 32, 32, SBK, 2, 2, true>, C, ldc, A, a_rs, a_cs,
-                                  B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, kslice));
+      TNN_CUDA(launch_small(gemm_simt_kernel<T, 32, 32, SBK, 2, 2, true>, grid, dim3(256), st, true, (unsigned)S,
+                            C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src,
+                            kslice));
       ctx().launches++;
       prof_end(2);
       return 0;
     }
-    gemm_simt_kernel<T, 32, 32, SBK, 2, 2, false><<<grid, 256, 0, st>>>(C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src, 0);
+    TNN_CUDA(launch_small(gemm_simt_kernel<T, 32, 32, SBK, 2, 2, false>, grid, dim3(256), st, true, 1u,
+                          C, ldc, A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, bias, flags, act_out, mask_src,
+                          (int64_t)0));
+    ctx().launches++;
+    prof_end(2);
+    return 0;
   }
   TNN_POST_LAUNCH();
   prof_end(2);
@@ -361,8 +357,9 @@ static int dense_bwd_impl(const T* g, const T* x, const T* w, const T* mask, T* 
   add(db, N, nullptr, 0, 0, g, N, 1, 1, N, Bn, db_acc ? 1 : 0, nullptr, nullptr);      // 1^T @ g
   constexpr int SBK = sizeof(T) == 4 ? 128 : 64;
   prof_begin(2);
-  gemm_simt_group_kernel<T, SBK><<<next, 256, 0, ctx().stream>>>(grp);
-  TNN_POST_LAUNCH();
+  TNN_CUDA(launch_small(gemm_simt_group_kernel<T, SBK>, dim3((unsigned)next), dim3(256), ctx().stream, true, 1u,
+                        grp));
+  ctx().launches++;
   prof_end(2);
   return 0;
 }
