@@ -344,3 +344,33 @@ def test_programmatic_dependent_launch_is_bit_identical():
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
         out[flag] = json.loads(line[len("RESULT "):])
     assert out["0"] == out["1"]
+
+
+def test_gradient_accumulation_over_prefetched_batches():
+    """a loop that is NOT the five lines: backward() on two consecutive PrefetchIterator batches,
+    then one step().  The first batch's postponed lines must run before the iterator reuses that
+    batch's device buffers (the iterator flushes them when it is resumed); same bits as the eager
+    engine"""
+    from core.losses import SoftmaxCrossEntropyLoss
+    from utils.data_iterator import PrefetchIterator
+    rng = np.random.RandomState(6)
+    n, D, C = 64 * 12, 40, 6
+    x = rng.rand(n, D).astype(np.float32)
+    lab = rng.randint(0, C, n)
+    res = {}
+    for defer in (False, True):
+        net, model = _model([24, C], 13, D, defer=defer, fuse=False)
+        ce = SoftmaxCrossEntropyLoss()
+        losses = []
+        for i, batch in enumerate(PrefetchIterator(batch_size=64, num_classes=C)(x, lab)):
+            if i % 2 == 0:
+                model.zero_grad()
+            loss = ce.loss(model.forward(batch.inputs), batch.targets)
+            loss.backward()
+            if i % 2 == 1:
+                model.step()
+            losses.append(float(loss.values) if i % 3 == 0 else None)
+        res[defer] = (losses, _params(net))
+    assert res[False][0] == res[True][0]
+    for pa, pb in zip(res[False][1], res[True][1]):
+        assert np.array_equal(pa, pb)

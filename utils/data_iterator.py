@@ -113,6 +113,7 @@ class PrefetchIterator(BaseIterator):
 
     def __call__(self, inputs, targets):
         import core._backend as be
+        import core.tensor as T
         from core.tensor import Tensor
         inputs = np.require(inputs, np.float32, "C")
         if self.num_classes is None:
@@ -165,4 +166,7 @@ class PrefetchIterator(BaseIterator):
             yield Batch(inputs=Tensor(xv), targets=Tensor(yv))
             if last:
                 return
+            # a training iteration the engine postponed (core/_deferred.py) and the loop did not
+            # finish with step() still names this batch's buffers, which the next stage() reuses
+            T._flush_deferred()
             step += 1
