@@ -283,8 +283,11 @@ class Model(object):
 
     def _step_key(self, x, y, loss_obj, kind="train_step"):
         # (loss objects of one class without state are interchangeable: run.py:72-73 builds two)
+        # the layer list is part of the key: swapping an activation leaves every parameter where it
+        # was, but a recording of the old network must not be replayed for the new one
         return (kind, x.shape, x.dtype.str, y.shape, y.dtype.str, dist.world_size(), id(self.optimizer),
-                type(loss_obj), id(getattr(loss_obj, "_weight", None)), self._phase)
+                type(loss_obj), id(getattr(loss_obj, "_weight", None)), self._phase,
+                tuple((id(layer), type(layer)) for layer in self.net.layers))
 
     def _step_generic(self):
         """the reference's three stages verbatim (model.py:45-61), on device arrays"""
@@ -505,6 +508,7 @@ class _CapturedStep(object):
         self.y = be.empty(y.shape, y.dtype)
         self.hyper = be.zeros((8,), be.F64)
         self.plist = model._param_list()
+        self.layers = list(model.net.layers)   # kept alive: their ids are part of the recording's key
         opt = model.optimizer
         self.graph = be.StepGraph()
         for dt in (be.F32, be.F64):

@@ -374,3 +374,30 @@ def test_gradient_accumulation_over_prefetched_batches():
     assert res[False][0] == res[True][0]
     for pa, pb in zip(res[False][1], res[True][1]):
         assert np.array_equal(pa, pb)
+
+
+def test_a_changed_layer_list_is_not_served_by_an_old_recording():
+    """swapping an activation between iterations leaves every parameter in place (the arena stays
+    valid) but changes the network: the recording of the old layer list must not be replayed --
+    the loop and train_step both give the eager engine's bits"""
+    from core.layers import Tanh
+    batches = _batches(40, 6, [32] * 12, seed=8)
+    res = {}
+    for mode in ("eager", "loop", "train_step"):
+        net, model = _model([24, 16, 6], 17, 40, defer=(mode == "loop"), fuse=False)
+        model.fuse_small_mlp = False
+        losses = []
+        for i, (x, y) in enumerate(batches):
+            if i == 6:
+                net.layers[1] = Tanh()
+            if mode == "train_step":
+                losses.append(float(model.train_step(x, y).values))
+            else:
+                losses += [float(v) for v in _loop(model, [(x, y)])]
+        res[mode] = (losses, _params(net))
+        if mode != "eager":
+            assert len(_recordings(model)) == 2
+    for mode in ("loop", "train_step"):
+        assert res["eager"][0] == res[mode][0], mode
+        for pa, pb in zip(res["eager"][1], res[mode][1]):
+            assert np.array_equal(pa, pb)
