@@ -638,7 +638,7 @@ def run_b200_arm(args, cfg):
                     "ms_per_step": e2e_ms / e2e_steps,
                     "ms_per_step_runs": [r / e2e_steps for r in e2e_runs],
                     "pipeline": "PrefetchIterator: float32 inputs + int32 labels from pinned host "
-                                "memory on a copy stream, one-hot rows built on the device; every "
+                                "memory on a copy stream, the fused cross-entropy reads the class indices (no dense one-hot rows); every "
                                 "step's loss is read back to the host one step behind"},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": last_loss,
             "gemm_tflops_algorithmic": flops_step * args.steps / (ms * 1e-3) / 1e12,
