@@ -295,3 +295,109 @@ def test_reference_format_checkpoint_unpickles_without_a_gpu():
     shapes = [tuple(_pickled_values(layer.params[k]).shape) for layer in net.layers
               for k in ("w", "b") if getattr(layer, "params", None)]
     assert shapes == [(4, 3), (1, 3), (3, 2), (1, 2)]
+
+
+def test_postponed_iteration_state_machine_without_a_gpu():
+    """core/_deferred.py on stand-in tensors (no device): the five lines are only noted; any other
+    use runs them in order (forward, loss, backward) exactly once; the lazy objects BECOME the
+    computed tensors (identity kept, class switched); reading a parameter's gradient, or starting
+    another iteration, flushes the pending one; a replayed step hands out loss and prediction"""
+    import types
+    import core._deferred as D
+    import core.tensor as T
+    from core.tensor import Tensor
+
+    class FakeArray(object):
+        def __init__(self, shape, tag):
+            self.shape, self.dtype, self.tag, self.size = shape, np.dtype(np.float32), tag, int(np.prod(shape))
+
+    def fake_tensor(shape, tag, requires_grad=True):
+        t = Tensor.__new__(Tensor)
+        t.__dict__.update(_data=FakeArray(shape, tag), _host=None, _grad=None, _grad_zero=requires_grad,
+                          _grad_host=None, _gslot=None, _relu_pre=None, _fused_bwd=None,
+                          requires_grad=requires_grad, dependency=[])
+        return t
+
+    calls = []
+
+    class Net(object):
+        def forward(self, x):
+            calls.append("forward")
+            return fake_tensor((4, 3), "pred")
+
+    class Loss(object):
+        _weight = None
+
+        def loss(self, pred, y):
+            assert type(pred) is Tensor and pred._data.tag == "pred"      # already adopted
+            calls.append("loss")
+            out = fake_tensor((), "loss")
+            out.backward = lambda grad=None: calls.append("backward")
+            return out
+
+    model = types.SimpleNamespace(net=Net(), _note_output=lambda x, out: None)
+    x, y = fake_tensor((4, 5), "x", False), fake_tensor((4, 3), "y", False)
+    T._DEFERRED[0] = None
+
+    # --- the five lines are only noted
+    pred = D.begin(model, x, (4, 3), np.dtype(np.float32))
+    assert type(pred) is D.LazyTensor and pred.shape == (4, 3) and pred.ndim == 2 and pred.requires_grad
+    loss = D.defer_loss(Loss(), pred, y)
+    assert type(loss) is D.LazyTensor and loss.shape == ()
+    loss.backward()
+    chain = T._DEFERRED[0]
+    assert chain is not None and chain.stage == "backward" and calls == []
+
+    # --- a parameter's gradient is read: the postponed lines run, in order, once
+    param = fake_tensor((5, 3), "w")
+    g = param.grad
+    assert g.shape == (5, 3) and calls == ["forward", "loss", "backward"] and T._DEFERRED[0] is None
+    assert type(pred) is Tensor and pred._data.tag == "pred" and type(loss) is Tensor and loss._data.tag == "loss"
+    chain.materialise()
+    assert calls == ["forward", "loss", "backward"]                  # idempotent
+
+    # --- touching the prediction first: only the forward runs; the loss is then computed eagerly
+    del calls[:]
+    pred = D.begin(model, x, (4, 3), np.dtype(np.float32))
+    assert pred._data.tag == "pred" and calls == ["forward"] and type(pred) is Tensor
+    assert D.defer_loss(Loss(), pred, y) is None                     # not a pending prediction any more
+
+    # --- a second iteration started while one is pending flushes the first
+    del calls[:]
+    p1 = D.begin(model, x, (4, 3), np.dtype(np.float32))
+    l1 = D.defer_loss(Loss(), p1, y)
+    p2 = D.begin(model, x, (4, 3), np.dtype(np.float32))
+    assert calls == ["forward", "loss"] and type(p1) is Tensor and type(l1) is Tensor
+    assert type(p2) is D.LazyTensor and T._DEFERRED[0].pred is p2
+
+    # --- things that are not the pattern are refused (and fall through to the eager code)
+    assert D.defer_loss(Loss(), p2, fake_tensor((4, 2), "y2", False)) is None     # other label shape
+    weighted = Loss()
+    weighted._weight = np.ones(3)
+    assert D.defer_loss(weighted, p2, y) is None
+    l2 = D.defer_loss(Loss(), p2, y)
+    del calls[:]
+    l2.backward(2.0)                                                 # a seeded backward is not postponed
+    assert calls == ["forward", "loss", "backward"] and T._DEFERRED[0] is None
+
+    # --- a replayed step serves its results
+    p3 = D.begin(model, x, (4, 3), np.dtype(np.float32))
+    l3 = D.defer_loss(Loss(), p3, y)
+    l3.backward()
+    chain = T._DEFERRED[0]
+    T._DEFERRED[0] = None                                            # Model.step() takes the chain over
+    step = types.SimpleNamespace(prediction_source=lambda: (FakeArray((4, 3), "logits"), FakeArray((4, 3), "dz")))
+    import core._backend as be
+    orig = (be.clone, be.ones_scalar)
+    be.clone = lambda a: FakeArray(a.shape, a.tag + "-copy")
+    be.ones_scalar = lambda dt: FakeArray((), "one")
+    try:
+        del calls[:]
+        D.serve_after_replay(chain, step, FakeArray((), "loss-value"))
+        assert type(l3) is Tensor and l3._data.tag == "loss-value" and l3._grad.tag == "one"
+        assert type(p3) is D.LazyTensor and step.live_prediction() is p3
+        D.pin_live_prediction(step)                                  # the next replay is about to run
+        assert type(p3) is Tensor and p3._data.tag == "logits-copy" and p3._grad.tag == "dz-copy"
+        assert p3.dependency == [] and calls == [] and step.live_prediction is None
+    finally:
+        be.clone, be.ones_scalar = orig
