@@ -274,6 +274,34 @@ def softmax_cross_entropy(logits, labels):
     return nll.sum() / m
 
 
+def cross_entropy_from_class_indices(logits, class_idx):
+    """The same loss and dL/dz for targets given as class indices (what the engine's fused kernels
+    read when a batch's one-hot rows were never written, tnn_ce_loss / tnn_ce_bwd `labels_dev`),
+    in plain numpy at the logits' precision: with y_i = one_hot(c_i) the row sum of losses.py:28,
+    sum_j p_ij y_ij, has the single non-zero term p_{i,c_i}, and adding exact zeros to it changes
+    no bit.  Returns (loss, dz); an index outside [0, C) behaves like an all-zero row (q_i = 0)."""
+    z = np.asarray(logits)
+    m, C = z.shape
+    e = np.exp(z - z.max())
+    p = e / e.sum()
+    idx = np.asarray(class_idx)
+    ok = (idx >= 0) & (idx < C)
+    q = np.zeros(m, z.dtype)
+    q[ok] = p[np.arange(m)[ok], idx[ok]]
+    with np.errstate(divide="ignore"):
+        loss = (-np.log(q)).sum() / m
+    dz = p.copy()
+    rows = np.arange(m)[ok]
+    # d/dz of -(1/m) sum_i ln q_i  with q_i = p_{i,c_i}:  p_ij * (#valid rows)/m ... spelled out as the
+    # chain rule the autograd graph of losses.py:24-32 applies: dL/dp_{i,c_i} = -1/(m q_i), then the
+    # quotient and exp/max nodes.  Closed form for one-hot rows: dz = k p - y/m with k = (#rows with a
+    # valid index)/m, because sum_ij (dL/dp_ij) p_ij = -k.
+    k = z.dtype.type(ok.sum()) / z.dtype.type(m)
+    dz = k * p
+    dz[rows, idx[ok]] -= z.dtype.type(1) / z.dtype.type(m)
+    return loss, dz
+
+
 # --------------------------------------------------------------------------------------------
 # optimisers (optimizer.py)
 # --------------------------------------------------------------------------------------------

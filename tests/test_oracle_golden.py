@@ -291,3 +291,31 @@ def test_allreduce_chunk_bounds():
         assert b[0][0] == 0 and b[-1][1] == n and len(b) <= chunks
         assert all(lo % align == 0 for lo, _ in b)
         assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+
+
+def test_cross_entropy_from_class_indices_equals_the_dense_form(golden_dir):
+    """the oracle's statement behind the engine's class-index path (tnn_ce_loss / tnn_ce_bwd
+    `labels_dev`): for one-hot targets the row sum of losses.py:28 is the single term p_{i,c_i}.
+    Checked against the goldens the REAL reference produced for the dense form (same inputs, labels
+    recovered with argmax) and bit for bit against the dense oracle's loss"""
+    gold = np.load(os.path.join(golden_dir, "ops.npz"))
+    for case in op_cases.CASES:
+        if case["op"] != "ce":
+            continue
+        (z, dense), rng = op_cases.make_inputs(case)
+        idx = np.argmax(dense, axis=1)
+        seed = rng.standard_normal(()).astype(z.dtype)          # the upstream gradient the golden used
+        loss, dz = R.cross_entropy_from_class_indices(z, idx)
+        ref_loss = R.softmax_cross_entropy(R.RefTensor(z), dense)
+        if z.dtype == np.float64:
+            assert loss == ref_loss.values                       # adding exact zeros changes no bit
+        else:                                                    # (the reference leaves float32 on the way)
+            assert abs(float(loss) - float(ref_loss.values)) <= 1e-6 * abs(float(ref_loss.values))
+        tol = 1e-12 if z.dtype == np.float64 else 1e-5
+        g_out, g_dz = gold[case["name"] + "/out"], gold[case["name"] + "/g0"]
+        assert abs(float(loss) - float(g_out)) <= tol * abs(float(g_out))
+        assert np.max(np.abs(dz * seed - g_dz)) <= tol * np.max(np.abs(g_dz))
+    # an index outside [0, C) is an all-zero row: q = 0, loss = +inf (as -log(0) in the dense form)
+    z = np.zeros((3, 4))
+    loss, _ = R.cross_entropy_from_class_indices(z, np.array([1, 7, 2]))
+    assert np.isinf(loss)
