@@ -73,7 +73,7 @@ class Model(object):
         if x._data.size > self.defer_loop_max_batch_elems:
             return False
         opt = self.optimizer
-        if opt.opt_code is None or not opt.uses_builtin_rule():
+        if not _builtin_rule(opt):
             return False
         plist = self._param_list()
         if not plist or not self._arena_valid(plist):
@@ -206,7 +206,7 @@ class Model(object):
         # overrides the reference's extension points (_compute_step / compute_step) goes through
         # compute_step(), consistently from its first step on (its state then has the reference's
         # unpadded flat layout)
-        fused = self.optimizer.uses_builtin_rule() and (
+        fused = _builtin_rule(self.optimizer) and (
             self._arena_valid(plist) or self._build_arena(plist))
         if fused:
             for p in plist:
@@ -367,9 +367,7 @@ class Model(object):
     def _capture_step(self, x, y, key, loss_obj=None, allow_fused=True):
         loss_obj = loss_obj or self.loss
         plist = self._param_list()
-        if not (plist and self._arena_valid(plist)) or self.optimizer.opt_code is None:
-            return None
-        if not self.optimizer.uses_builtin_rule():
+        if not (plist and self._arena_valid(plist)) or not _builtin_rule(self.optimizer):
             return None
         plan = self._fused_mlp_plan(x, y, loss_obj) if (self.fuse_small_mlp and allow_fused) else None
         if plan is not None:
@@ -479,6 +477,14 @@ class Model(object):
             return
         for p in plist:
             p.zero_grad()
+
+
+def _builtin_rule(opt):
+    """one of core/optimizer.py's fused update rules, not overridden -- False also for an optimiser
+    object that merely offers the reference's compute_step() (model.py:55) without deriving from
+    BaseOptimizer"""
+    check = getattr(opt, "uses_builtin_rule", None)
+    return getattr(opt, "opt_code", None) is not None and check is not None and bool(check())
 
 
 def _pickled_values(t):

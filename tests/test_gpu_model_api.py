@@ -267,3 +267,34 @@ def test_values_async_matches_values():
         assert np.array_equal(rm.result(), w)
         assert abs(float(rs.result()) - float(w.astype(np.float64).sum())) <= 1e-3 * abs(float(w.sum()))
         assert rm.result() is rm.result()          # cached after the first wait
+
+
+def test_optimizer_that_only_offers_compute_step():
+    """an optimiser object that does not derive from BaseOptimizer and offers just what the
+    reference's Model.step calls (model.py:55 `compute_step(grads, params)` -> per-layer dicts of
+    steps): Model.step applies its steps, nothing is postponed or recorded for such a model"""
+    from core.tensor import Tensor
+
+    class Plain(object):
+        def compute_step(self, grads, params):
+            return [{k: -0.05 * (g.numpy() if hasattr(g, "numpy") else np.asarray(g)) for k, g in layer.items()}
+                    for layer in grads]
+
+    x, y = _data()
+    np.random.seed(4)
+    net, model = _mlp([13, 10], Plain())
+    losses = []
+    for _ in range(4):
+        before = [p.values.copy() for p in _params(net)] if net.layers[0].is_init else None
+        model.zero_grad()
+        pred = model.forward(Tensor(x))
+        assert type(pred) is Tensor
+        loss = model.loss.loss(pred, Tensor(y))
+        loss.backward()
+        grads = [p.grad.copy() for p in _params(net)]
+        model.step()
+        if before is not None:
+            for b, g, p in zip(before, grads, _params(net)):
+                assert np.allclose(p.values, b - 0.05 * g, atol=1e-7)
+        losses.append(float(loss.values))
+    assert losses[-1] < losses[0] and not model._captured
