@@ -123,7 +123,7 @@ _SIGNATURES = {
     "tnn_ce_stats": [_c_int, _c_vp, _c_i64, _c_i64, _c_vp],
     "tnn_ce_merge_stats": [_c_int, _c_vp, _c_vp, _c_int],
     "tnn_ce_loss": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_dbl, _c_vp, _c_vp, _c_vp],
-    "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp],
+    "tnn_ce_fwd_small": [_c_int, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_dbl, _c_vp, _c_vp, _c_vp, _c_vp],
     "tnn_ce_bwd": [_c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_dbl, _c_vp, _c_vp,
                    _c_vp],
     "tnn_set_gemm_reserved_sms": [_c_int],
@@ -1198,14 +1198,23 @@ def ce_small_ok(B, C):
     return B <= 2048 and B * C <= 16384
 
 
-def ce_fwd_small(z, y, m_global):
-    """stats, loss and q of a small logits matrix in one launch"""
+def ce_fwd_small(z, y, m_global, want_dz=False):
+    """stats, loss and q of a small logits matrix in one launch; with want_dz also dL/dz for the
+    upstream gradient 1 (returned fourth, else None): what ce_bwd would compute from backward()'s
+    default seed, bit for bit"""
     B, C = z.shape
     stats, q, loss = empty((2,), z.dtype), empty((B,), z.dtype), empty((), z.dtype)
+    dz = empty((B, C), z.dtype) if want_dz else None
     if _lib.tnn_ce_fwd_small(_DT_CODE[z.dtype], z.ptr, _DT_CODE[y.dtype], y.ptr, B, C,
-                             float(m_global), stats.ptr, q.ptr, loss.ptr):
+                             float(m_global), stats.ptr, q.ptr, loss.ptr, dz.ptr if want_dz else None):
         _raise("tnn_ce_fwd_small")
-    return stats, loss, q
+    return stats, loss, q, dz
+
+
+def is_ones_scalar(g):
+    """is this the shared constant backward() seeds a scalar loss with"""
+    one = _ONES.get(np.dtype(g.dtype))
+    return one is not None and g is one
 
 
 def ce_bwd(z, y, stats, q, m_global, g):

@@ -327,7 +327,10 @@ int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B,
 /* stages 1 + 2 in ONE single-CTA launch for small logits (B <= 2048, B*C <= 16384: the
  * examples/mnist 128 x 10 case), single process only; same arithmetic and order as the staged path */
 int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-                     double m_global, void* stats_dev, void* q_dev, void* loss_dev);
+                     double m_global, void* stats_dev, void* q_dev, void* loss_dev,
+                     void* dz_dev /* optional [B,C]: dL/dz for the upstream gradient 1 (the seed of
+                                     loss.backward(), tensor.py:160), bit-identical to tnn_ce_bwd with
+                                     g = 1 -- the step's backward pass then skips that launch */);
 int tnn_ce_bwd(int dtype, void* dz, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
                const void* stats_dev, const void* q_dev, double m_global, const void* g_dev,
                void* stat_meta /* optional, float32: a zeroed f16 operand record (tnn_f16_meta_reset)

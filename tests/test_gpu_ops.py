@@ -71,12 +71,16 @@ def test_ce_single_launch_forward_equals_staged(shape, zdt, ydt):
     z = be.from_numpy((rng.standard_normal((B, C)) * 3).astype(zdt))
     y = be.from_numpy(np.eye(C)[rng.randint(0, C, B)].astype(ydt))
     assert be.ce_small_ok(B, C)
-    stats1, loss1, q1 = be.ce_fwd_small(z, y, B)
+    stats1, loss1, q1, dz1 = be.ce_fwd_small(z, y, B, want_dz=True)
     stats2 = be.ce_stats(z)
     loss2, q2 = be.ce_loss(z, y, stats2, B)
     assert np.array_equal(stats1.numpy(), stats2.numpy())
     assert np.array_equal(q1.numpy(), q2.numpy())
     assert np.array_equal(loss1.numpy(), loss2.numpy())
+    # ... and the dL/dz it leaves for backward()'s default seed is what the backward kernel writes
+    dz2 = be.ce_bwd(z, y, stats2, q2, B, be.ones_scalar(z.dtype))
+    assert np.array_equal(dz1.numpy(), dz2.numpy())
+    assert be.ce_fwd_small(z, y, B)[3] is None
 
 
 def test_ce_soft_labels(engine):

@@ -339,7 +339,7 @@ __device__ __forceinline__ T block1024_reduce_first8(T v, T* sm /* >= 32 */) {
 constexpr int CE_SMALL_STAGE_BYTES = 16384;   // logits staged in shared memory when they fit (MNIST: 1280 values)
 template <typename T, typename TY>
 __global__ void __launch_bounds__(1024)
-ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats, T* q, T* loss) {
+ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats, T* q, T* loss, T* dz_out) {
   __shared__ T sm[32];
   __shared__ T nll[CE_SMALL_MAX_ROWS];
   constexpr int CE_SMALL_STAGE = CE_SMALL_STAGE_BYTES / (int)sizeof(T);
@@ -401,6 +401,20 @@ ce_fwd_small_kernel(const T* z, const TY* y, int64_t B, int64_t C, T m, T* stats
     for (int64_t i = threadIdx.x; i < B; i += 256) s += nll[i];
   s = block1024_reduce_first8<T, false>(s, sm);
   if (threadIdx.x == 0) loss[0] = s / m;
+  if (dz_out == nullptr) return;
+  // dL/dz for the upstream gradient 1 (what loss.backward() seeds): ce_bwd_kernel's expressions,
+  // operand for operand, so the bits are the ones that kernel would write with g = 1 -- the backward
+  // pass of a step then needs no cross-entropy launch at all (q of this CTA is visible after the
+  // barrier above)
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const int64_t r = i / C;
+    const T qm = q[r] * m;
+    const T yv = (T)y[i];
+    const T p = m_exp(zz[i] - mx) / S;
+    T v = p;
+    if (yv != T(0)) v = p - (yv * p) / qm;
+    dz_out[i] = v;
+  }
 }
 
 // ---- cross entropy backward ---------------------------------------------------------------------
@@ -755,19 +769,19 @@ int tnn_ce_loss(int dtype, const void* z, int y_dtype, const void* y, int64_t B,
 }
 
 int tnn_ce_fwd_small(int dtype, const void* z, int y_dtype, const void* y, int64_t B, int64_t C,
-                     double m_global, void* stats_dev, void* q_dev, void* loss_dev) {
+                     double m_global, void* stats_dev, void* q_dev, void* loss_dev, void* dz_dev) {
   TNN_REQUIRE_INIT();
   if (B <= 0 || C <= 0) TNN_FAIL("tnn_ce_fwd_small: empty logits");
   if (B > CE_SMALL_MAX_ROWS || B * C > 16384) TNN_FAIL("tnn_ce_fwd_small: at most 2048 rows and 16384 logits");
   cudaStream_t st = ctx().stream;
   if (dtype == TNN_F32 && y_dtype == TNN_F32)
-    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, float>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const float*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev));
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, float>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const float*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev, (float*)dz_dev));
   else if (dtype == TNN_F32 && y_dtype == TNN_F64)
-    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, double>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const double*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev));
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<float, double>, dim3(1), dim3(1024), st, true, 1u, (const float*)z, (const double*)y, B, C, (float)m_global, (float*)stats_dev, (float*)q_dev, (float*)loss_dev, (float*)dz_dev));
   else if (dtype == TNN_F64 && y_dtype == TNN_F64)
-    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, double>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const double*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev));
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, double>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const double*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev, (double*)dz_dev));
   else if (dtype == TNN_F64 && y_dtype == TNN_F32)
-    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, float>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const float*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev));
+    TNN_CUDA(launch_small(ce_fwd_small_kernel<double, float>, dim3(1), dim3(1024), st, true, 1u, (const double*)z, (const float*)y, B, C, m_global, (double*)stats_dev, (double*)q_dev, (double*)loss_dev, (double*)dz_dev));
   else
     TNN_FAIL("tnn_ce_fwd_small: bad dtype");
   TNN_POST_LAUNCH();
