@@ -5,7 +5,7 @@ examples/mnist/run.py:78-83 writes every iteration as
     model.zero_grad(); pred = model.forward(x); loss = loss_layer.loss(pred, y)
     loss.backward(); model.step()
 
-On this engine that is 13 launches of 4-10 us kernels and the loop is bound by the host's cost per
+On this engine that is a dozen launches of 4-10 us kernels and the loop is bound by the host's cost per
 launch.  `Model.train_step` records the same iteration into a CUDA graph, but it is a new entry
 point the unmodified example does not call.  This module lets the five lines themselves reach the
 recording: inside a training loop `Model.forward` hands back a Tensor whose values have not been
