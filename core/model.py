@@ -15,6 +15,7 @@ import numpy as np
 import core._backend as be
 import core._deferred as deferred
 import core._dist as dist
+import core.ops as ops
 import core.tensor as T
 
 _ALIGN = 64  # elements; keeps every parameter slot 256-byte aligned for 128-bit kernels / TMA
@@ -25,17 +26,17 @@ class Model(object):
     # train_step on a small Dense/ReLU MLP with SoftmaxCrossEntropyLoss (the examples/mnist network)
     # records the fused small-MLP pass (csrc/mlp_fused.cu) instead of the layer-by-layer step
     fuse_small_mlp = True
-    # the five-line loop of run.py:78-83 reaches the recorded step on its own (core/_deferred.py)
+    # the five-line loop of run.py:78-83 reaches the recorded step on its own (core/_deferred.py) ...
     defer_loop = deferred.ENABLED
-    # ... for launch-bound steps only: batch (inputs + targets) and parameter counts up to these many
-    # elements.  A wide step gains nothing from a replay (measured: 7.91 vs 7.92 ms for the 4 x 4096
-    # MLP) and its recording would pin the step's temporaries.
-    # the loop's recording is the layer-by-layer one (bit-identical to the eager lines); True lets it
-    # be the fused small-MLP pass where that applies (rounding-level differences, see train_step)
+    # ... as the layer-by-layer recording (bit-identical to the eager lines); True lets it be the fused
+    # small-MLP pass where that applies (rounding-level differences, see train_step)
     defer_loop_may_fuse = False
-    defer_loop_max_recordings = 8     # distinct batch shapes a loop may have recorded at a time
+    # ... for launch-bound steps only: batch and parameter counts up to these many elements.  A wide
+    # step gains nothing from a replay (measured: 7.91 vs 7.92 ms for the 4 x 4096 MLP) and its
+    # recording would pin the step's temporaries
     defer_loop_max_batch_elems = 1 << 22
     defer_loop_max_param_elems = 1 << 23
+    defer_loop_max_recordings = 8     # distinct batch shapes a loop may have recorded at a time
 
     def __init__(self, net, loss, optimizer):
         self.net = net
@@ -68,7 +69,7 @@ class Model(object):
         Parameters in their arena with freshly zeroed gradients (zero_grad() was the first line), a
         built-in update rule, an input that needs no gradient, and no earlier failure to record
         this batch shape."""
-        if x.requires_grad or (x.shape, x.dtype.str) in self._noloop:
+        if x.requires_grad or (x.shape, x.dtype.str) in self._noloop or not ops._GRAD_ENABLED:
             return False
         if x._data.size > self.defer_loop_max_batch_elems:
             return False
@@ -88,7 +89,6 @@ class Model(object):
     def predict(self, inputs):
         """forward pass without an autograd graph (the evaluation at run.py:87-91): activations are
         released as soon as the next layer has consumed them.  Not in the reference's interface."""
-        import core.ops as ops
         from core.tensor import Tensor
         x = inputs if isinstance(inputs, Tensor) else Tensor(inputs)
         with ops.no_grad():
